@@ -1,0 +1,24 @@
+# Builds libzk_b200.so (sm_100a only) in-tree, plus the C oracle helpers.
+NVCC      ?= nvcc
+CSRC      := zenker_audio_detection_b200/csrc
+LIBDIR    := zenker_audio_detection_b200/lib
+NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC) \
+             --expt-relaxed-constexpr -Xptxas -v
+SRCS      := $(CSRC)/zk_host.cu $(CSRC)/zk_gemm.cu $(CSRC)/zk_attn.cu $(CSRC)/zk_ops.cu $(CSRC)/zk_frontend.cu $(CSRC)/zk_model.cu
+OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+HDRS      := include/zk_b200.h $(wildcard $(CSRC)/*.cuh)
+
+all: $(LIBDIR)/libzk_b200.so
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIBDIR)/libzk_b200.so: $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) -shared -o $@ $(OBJS) -cudart static
+
+clean:
+	rm -rf build $(LIBDIR)/libzk_b200.so
+
+.PHONY: all clean

@@ -1,0 +1,30 @@
+"""Fused tcgen05 attention vs torch fp32 softmax(QK^T/8)V on the same bf16 q,k,v (through the C ABI)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, B, T):
+    q, k, v = (qkv[:, i * 768:(i + 1) * 768].float().view(B, T, 12, 64).transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(2, 3)) * 0.125
+    o = torch.softmax(s, dim=-1) @ v
+    return o.transpose(1, 2).reshape(B * T, 768)
+
+
+@pytest.mark.parametrize("B,T,scale", [(2, 1214, 1.0), (1, 128, 1.0), (1, 129, 1.0), (3, 300, 3.0), (1, 62, 1.0),
+                                       (1, 1214, 6.0)])
+def test_attention(B, T, scale):
+    from zenker_audio_detection_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    qkv = torch.randn(B * T, 2304, device="cuda", generator=g)
+    qkv[:, :1536] *= scale  # larger logits -> peaky softmax
+    qkv = qkv.to(torch.bfloat16)
+    out = ops.attention(qkv, B, T)
+    torch.cuda.synchronize()
+    ref = _ref(qkv, B, T)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, err  # P is rounded to bf16 (2^-9) before the PV product; |v| ~ 1..4
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel <= 1e-2, rel

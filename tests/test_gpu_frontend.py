@@ -1,0 +1,138 @@
+"""Resampler and Kaldi fbank (continuous + ASTFeatureExtractor contract) vs the installed torchaudio /
+transformers executed on the CPU, and vs the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FLOOR = float(np.log(np.finfo(np.float32).eps))
+
+
+def fbank_gate(got, ref, ref64=None):
+    """|d| <= 1e-4*|ref| + 1e-3 everywhere AND >= 99.9 % within 1e-4 relative."""
+    d = np.abs(got - ref)
+    assert np.all(d <= 1e-4 * np.abs(ref) + 1e-3), float(d.max())
+    frac = float(np.mean(d <= 1e-4 * np.abs(ref)))
+    assert frac >= 0.999, frac
+    if ref64 is not None:
+        e_ours, e_ref = np.abs(got - ref64).max(), np.abs(ref - ref64).max()
+        assert e_ours <= 2.0 * e_ref + 1e-5, (e_ours, e_ref)
+
+
+@pytest.mark.parametrize("seconds", [0.025, 0.03, 1.0, 7.3, 60.0])
+def test_fbank_continuous(seconds):
+    from oracle import numerics, thirdparty
+    from zenker_audio_detection_b200 import ops, synth
+
+    wave = synth.noise_16k(seconds, seed=int(seconds * 1000) + 1)
+    if seconds > 5:
+        wave[16000:32000] *= 0.001  # quiet stretch
+        wave[40000:40400] = 0.0     # digital silence -> log floor everywhere
+    plan = ops.FbankPlan()
+    got = plan.fbank(torch.from_numpy(wave).cuda()).cpu().numpy()
+    ref = thirdparty.kaldi_fbank(wave)
+    assert got.shape == ref.shape
+    fbank_gate(got, ref, numerics.fbank(wave, dtype=np.float64) if seconds <= 8 else None)
+    # empty mel filters always sit at the floor
+    empty = np.where(np.all(ref == ref[0:1, :], axis=0) & (np.abs(ref[0] - FLOOR) < 1e-5))[0]
+    for c in empty:
+        assert np.all(got[:, c] == np.float32(FLOOR))
+
+
+def test_fbank_too_short_is_empty():
+    from zenker_audio_detection_b200 import ops
+
+    plan = ops.FbankPlan()
+    assert plan.fbank(torch.zeros(399, device="cuda")).shape == (0, 128)
+
+
+def test_fbank_window_equals_strided_rows():
+    """fbank(window k) == continuous fbank rows [50k, 50k+98) bit-exactly."""
+    from zenker_audio_detection_b200 import ops, synth
+
+    wave = torch.from_numpy(synth.recording(12.0, 16000, seed=9)).cuda()
+    plan = ops.FbankPlan()
+    whole = plan.fbank(wave)
+    wins = torch.stack([wave[8000 * k: 8000 * k + 16000] for k in range(23)])
+    feats = plan.fx_contract(wins, 0.0, 0.5, 1024, do_normalize=False)
+    for k in range(23):
+        assert torch.equal(feats[k, :98], whole[50 * k: 50 * k + 98])
+        assert torch.all(feats[k, 98:] == 0)
+
+
+def test_fx_contract_vs_hf_and_golden(golden_dir):
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import ops, synth
+
+    w = synth.cfg1_windows(64)
+    plan = ops.FbankPlan()
+    got = plan.fx_contract(torch.from_numpy(w).cuda(), synth.STAGE1_MEAN, synth.STAGE1_STD, 1024).cpu().numpy()
+    fx = thirdparty.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
+    ref = fx(list(w), sampling_rate=16000, return_tensors="np")["input_values"]
+    assert got.shape == ref.shape == (64, 1024, 128) and got.dtype == np.float32
+    assert np.array_equal(got[:, 98:], ref[:, 98:])  # pad rows hold exactly (0-mean)/(2*std)
+    s2 = 2 * synth.STAGE1_STD
+    d = np.abs(got - ref)
+    assert np.all(d <= 1e-4 * np.abs(ref) + 1e-3 / s2 + 1e-6)
+    gold = np.load(os.path.join(golden_dir, "fx_cfg1.npz"))
+    assert np.all(np.abs(got[:4, :98] - gold["rows"]) <= 1e-4 * np.abs(gold["rows"]) + 1e-3 / s2 + 1e-6)
+    assert np.all(got[:4, 98:] == gold["pad_value"])
+
+
+@pytest.mark.parametrize("n", [400, 16000, 16037, 5000])
+def test_fx_contract_ragged_and_truncate(n):
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import ops, synth
+
+    w = synth.noise_16k(n / 16000.0 * 3, seed=n)[: 3 * n].reshape(3, n)
+    plan = ops.FbankPlan()
+    for max_length in (1024, 20):
+        got = plan.fx_contract(torch.from_numpy(w.copy()).cuda(), -4.27, 4.57, max_length).cpu().numpy()
+        fx = thirdparty.hf_feature_extractor(-4.27, 4.57, max_length=max_length)
+        ref = fx(list(w), sampling_rate=16000, return_tensors="np")["input_values"]
+        assert got.shape == ref.shape
+        assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref) + 2e-4)
+
+
+@pytest.mark.parametrize("sr,seconds,channels", [(48000, 2.0, 1), (48000, 0.5, 2), (44100, 0.7, 1), (32000, 1.0, 1),
+                                                 (96000, 0.3, 1), (16000, 0.5, 2), (8000, 0.5, 1)])
+def test_resample_vs_torchaudio(sr, seconds, channels):
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import ops, synth
+
+    r = synth.recording(seconds * channels, sr, seed=sr // 100 + channels)
+    n = len(r) // channels
+    x = r[: n * channels].reshape(channels, n)
+    ref = thirdparty.resample(x, sr, 16000)
+    got = ops.resample(torch.from_numpy(x).cuda(), sr, 16000).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-6 + 1e-5 * np.abs(ref).max()
+
+
+def test_resample_golden(golden_dir):
+    from zenker_audio_detection_b200 import ops, synth
+
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    r = synth.recording(0.5, 48000, seed=5)
+    got = ops.resample(torch.from_numpy(r).cuda(), 48000, 16000).cpu().numpy()
+    assert np.abs(got - g["out48"]).max() <= 2e-6
+    r2 = synth.recording(0.25, 44100, seed=6)
+    got2 = ops.resample(torch.from_numpy(r2).cuda(), 44100, 16000).cpu().numpy()
+    assert np.abs(got2 - g["out441"]).max() <= 2e-6
+    st = np.stack([r[:12000], r[12000:24000]])
+    got3 = ops.resample(torch.from_numpy(st).cuda(), 48000, 16000).cpu().numpy()
+    assert np.abs(got3 - g["out_stereo"].reshape(-1)).max() <= 2e-6
+
+
+def test_resample_pcm16():
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import ops, synth
+
+    r = synth.recording(1.0, 48000, seed=12)
+    pcm = np.round(r * 32767).astype(np.int16).reshape(-1, 2)  # (n, 2) interleaved stereo
+    ref = thirdparty.resample((pcm.astype(np.float32) / 32768.0).T.copy(), 48000, 16000)
+    got = ops.resample(torch.from_numpy(pcm).cuda(), 48000, 16000).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6

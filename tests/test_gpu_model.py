@@ -1,0 +1,75 @@
+"""Full AST forward through the C ABI vs the fp32 oracle (numerics.ast_forward) and the HF golden logits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_logits(sd, feats, **kw):
+    from oracle import numerics
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        return numerics.ast_forward(sdc, feats.cuda(), **kw)
+
+
+def test_one_layer_hidden_state():
+    """1-layer model: the residual stream must match fp32 closely (pins token order, patch gather, pos-emb)."""
+    from zenker_audio_detection_b200 import ops, synth
+
+    sd = synth.random_state_dict(5)
+    plan = ops.FbankPlan()
+    w = torch.from_numpy(synth.cfg1_windows(4)).cuda()
+    feats = plan.fx_contract(w, synth.STAGE1_MEAN, synth.STAGE1_STD, 1024)
+    m = ops.AstModel(sd, num_layers=1)
+    logits, hidden = m.forward_features(feats, return_hidden=True)
+    ref_logits, ref_hidden = _oracle_logits(sd, feats, num_layers=1, return_hidden=True)
+    err = (hidden - ref_hidden).abs().max().item()
+    assert err <= 3e-2, err
+    assert (logits - ref_logits).abs().max().item() <= 1e-2
+
+
+def test_full_forward_vs_oracle_and_golden(golden_dir):
+    from zenker_audio_detection_b200 import ops, synth
+
+    gold = np.load(os.path.join(golden_dir, "ast_cfg1.npz"))
+    plan = ops.FbankPlan()
+    w = torch.from_numpy(synth.cfg1_windows(64)[:16]).cuda()
+    for seed, (mean, std), key, bkey in ((11, (synth.STAGE1_MEAN, synth.STAGE1_STD), "logits1", "head_bias1_s1"),
+                                         (22, (synth.STAGE2_MEAN, synth.STAGE2_STD), "logits2", "head_bias1_s2")):
+        sd = synth.random_state_dict(seed, head_bias1=float(gold[bkey]))
+        feats = plan.fx_contract(w, mean, std, 1024)
+        m = ops.AstModel(sd)
+        logits = m.forward_features(feats)
+        ref = _oracle_logits(sd, feats)
+        err = (logits - ref).abs().max().item()
+        gerr = np.abs(logits.cpu().numpy() - gold[key]).max()
+        print(f"seed {seed}: max |logit - fp32 oracle| = {err:.4g}; vs HF golden = {gerr:.4g}")
+        assert err <= 1e-2, err      # north_star: logits within 1e-2 absolute in bf16
+        assert gerr <= 1e-2, gerr
+        # fused path (gather from un-normalised per-window fbank laid out contiguously) gives the same logits
+        del m
+
+
+def test_fused_fbank_path_matches_contract_path():
+    from zenker_audio_detection_b200 import ops, synth
+
+    sd = synth.random_state_dict(11)
+    plan = ops.FbankPlan()
+    wave = torch.from_numpy(synth.recording(8.0, 16000, seed=3)).cuda()
+    fb = plan.fbank(wave)
+    nwin = (wave.numel() - 16000) // 8000 + 1
+    wins = torch.stack([wave[8000 * k: 8000 * k + 16000] for k in range(nwin)])
+    feats = plan.fx_contract(wins, synth.STAGE1_MEAN, synth.STAGE1_STD, 1024)
+    m = ops.AstModel(sd, num_layers=2)
+    a = m.forward_features(feats)
+    b = m.forward_fbank(fb, nwin, synth.STAGE1_MEAN, synth.STAGE1_STD)
+    assert torch.equal(a, b)
+    idx = torch.tensor([5, 2, 9], dtype=torch.int32, device="cuda")
+    c = m.forward_fbank(fb, 3, synth.STAGE1_MEAN, synth.STAGE1_STD, window_index=idx)
+    assert torch.equal(c, a[idx.long()])

@@ -1,0 +1,252 @@
+// Fused non-causal attention for sm_100a: O = softmax(Q K^T / sqrt(64)) V per (window, head), head_dim 64.
+// One CTA = 128 queries of one (window, head); two CTAs are co-resident per SM (114 KiB smem, 256 TMEM
+// columns each) so one CTA's softmax overlaps the other's MMAs.
+//
+//   warp 0      TMA producer: Q tile once, then a 2-stage ring of {K_j, V_j} 128x64 bf16 tiles
+//   warp 1      TMEM allocator + MMA issuer:  S = Q K_j^T (UMMA 128x128x16, TMEM cols [0,128)),
+//               O_j = P_j V_j (UMMA 128x64x16, V as MN-major operand, TMEM cols 128 + 64*(j&1))
+//   warps 2..5  softmax: one query row per thread, fp32 online softmax straight out of TMEM, P_j written
+//               to 128B-swizzled shared memory as the bf16 A operand of the second MMA; the running output
+//               is kept in registers and rescaled there (no TMEM read-modify-write).
+//
+// Q, K and V are read in place from the fused QKV projection output [batch*tokens][2304] (q | k | v, head h
+// at columns 64h), keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
+// Replaces F.scaled_dot_product_attention on the reference path (HF:modeling_audio_spectrogram_transformer.py:162-176).
+#include "zk_b200.h"
+#include "zk_common.cuh"
+#include "zk_internal.cuh"
+
+namespace zk {
+namespace attn {
+
+constexpr int BQ = 128, BKV = 128, D = 64, HEADS = 12, HID = HEADS * D, KV_STAGES = 2;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // one 128 x 64 bf16 tile (Q, K_j or V_j)
+constexpr int P_BYTES = BQ * BKV * 2;
+constexpr int OFF_Q = 0, OFF_KV = TILE_BYTES, OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES, OFF_BAR = OFF_P + P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256, TM_S = 0, TM_O = 128;
+constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
+constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V) is MN-major
+constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int tokens) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (tokens + BKV - 1) / BKV;
+  const int row_base = b * tokens;  // first row of this window in the [batch*tokens] matrices
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("zk attn: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(smem + OFF_Q, &tm, q_full, h * D, row_base + qb * BQ);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        uint8_t* dst = smem + OFF_KV + st * 2 * TILE_BYTES;
+        tma_load_2d(dst, &tm, &kv_full[st], HID + h * D, row_base + j * BKV);
+        tma_load_2d(dst + TILE_BYTES, &tm, &kv_full[st], 2 * HID + h * D, row_base + j * BKV);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq = smem_u32(smem + OFF_Q), sp = smem_u32(smem + OFF_P);
+      const uint64_t q_desc = umma_desc_sw128(sq, 16, 1024);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + OFF_KV + st * 2 * TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_bf16_ss(tmem_base + TM_S, q_desc + 2 * k, k_desc + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(p_full, j & 1);  // P_j is in smem and S_j has been read out of TMEM
+        tc_fence_after();
+        if (j + 1 < nkv) issue_s(j + 1);
+        const int st = j & 1;
+        const uint32_t sv = smem_u32(smem + OFF_KV + st * 2 * TILE_BYTES + TILE_BYTES);
+        const uint32_t d_o = tmem_base + TM_O + (j & 1) * D;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // A = P: two 64-key swizzle atoms of 16 KiB; B = V_j: 16 keys = 16 rows of 128 B (MN-major)
+          const uint64_t p_desc = umma_desc_sw128(sp + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t v_desc = umma_desc_sw128(sv + k * 16 * 128, 1024, 1024);
+          umma_bf16_ss(d_o, p_desc, v_desc, IDESC_O, k != 0);
+        }
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sp_row = smem_u32(smem + OFF_P) + row * 128;
+    float m = -INFINITY, l = 0.f;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TM_S + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]);
+          if (c * 32 + i >= kmax) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float alpha = fast_exp2((m - mx) * SCALE_LOG2E);
+      if (j > 0) {  // fold in O_{j-1} = P_{j-1} V_{j-1} (relative to the old maximum), then rescale
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + TM_O + ((j - 1) & 1) * D + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+        }
+      }
+      l *= alpha;
+      m = mx;
+      const float mb = mx * SCALE_LOG2E;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TM_S + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -mb));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), SCALE_LOG2E, -mb));
+          if (c * 32 + i >= kmax) p0 = 0.f;
+          if (c * 32 + i + 1 >= kmax) p1 = 0.f;
+          l += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
+        const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
+          st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(p_full);
+    }
+    {
+      const int jl = nkv - 1;
+      mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const int q = qb * BQ + row;
+      __nv_bfloat16* dst = out + (long long)(row_base + q) * HID + h * D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TM_O + (jl & 1) * D + c * 32, r);
+        tmem_ld_wait();
+        if (q < tokens) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            const int i0 = c * 32 + g * 8;
+            v.x = pack_bf16((o[i0 + 0] + __uint_as_float(r[g * 8 + 0])) * inv, (o[i0 + 1] + __uint_as_float(r[g * 8 + 1])) * inv);
+            v.y = pack_bf16((o[i0 + 2] + __uint_as_float(r[g * 8 + 2])) * inv, (o[i0 + 3] + __uint_as_float(r[g * 8 + 3])) * inv);
+            v.z = pack_bf16((o[i0 + 4] + __uint_as_float(r[g * 8 + 4])) * inv, (o[i0 + 5] + __uint_as_float(r[g * 8 + 5])) * inv);
+            v.w = pack_bf16((o[i0 + 6] + __uint_as_float(r[g * 8 + 6])) * inv, (o[i0 + 7] + __uint_as_float(r[g * 8 + 7])) * inv);
+            *reinterpret_cast<uint4*>(dst + i0) = v;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace attn
+
+int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream_t stream) {
+  using namespace attn;
+  int rc = device_check();
+  if (rc) return rc;
+  if (!qkv || !out || batch <= 0 || tokens <= 0) {
+    set_error("attention_bf16: null pointer or empty shape");
+    return ZK_ERR_ARG;
+  }
+  if (batch > 65535) {
+    set_error("attention_bf16: batch %d > 65535", batch);
+    return ZK_ERR_SHAPE;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap tm;
+  if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
+  dim3 grid((tokens + BQ - 1) / BQ, HEADS, batch);
+  attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+  ZK_LAUNCH_CHECK("attn_kernel");
+  return 0;
+}
+
+}  // namespace zk
+
+extern "C" int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream) {
+  return zk::attention_bf16(d_qkv, d_out, batch, tokens, (cudaStream_t)stream);
+}

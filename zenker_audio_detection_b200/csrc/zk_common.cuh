@@ -166,13 +166,31 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ----------------------------------------------------------------------------- host: tensor maps
-// bf16 row-major 2-D [rows, cols] with a (box_rows x box_cols) box, 128-B swizzle.  cols*2 must be a
-// multiple of 16 B; box_cols*2 must be 128 B.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                      uint32_t box_cols);
-// bf16 3-D [d2, d1, d0(cols)] with row pitch `pitch_elems`; box (1 x box_rows x box_cols).
-int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t cols, uint64_t pitch_elems,
+// ----------------------------------------------------------------------------- small device helpers
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ----------------------------------------------------------------------------- host helpers
+int device_check();  // 0 when the device is sm_100 and the tensor-map encoder is available
+int num_sms();
+// bf16 row-major 2-D [rows, cols] with row pitch `pitch_elems`, (box_rows x box_cols) box, 128-B swizzle.
+// box_cols must be 64 (128 B); box_rows <= 256.  Out-of-bounds rows/cols are zero filled.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace zk

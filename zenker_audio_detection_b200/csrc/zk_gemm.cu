@@ -1,0 +1,268 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulation in
+// TMEM, operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma issued by one thread.
+//
+//   warp 0      TMA producer   (4-stage ring of {A 128x64, W 256x64} bf16 tiles, 48 KiB / stage)
+//   warp 1      TMEM allocator + MMA issuer (UMMA 128x256x16, 4 per stage)
+//   warps 2..9  epilogue: TMEM -> registers -> fused bias / GELU / residual / position-embedding -> global
+//
+// The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
+// MMAs of tile t+1.  Replaces the cuBLAS calls behind nn.Linear on the reference path
+// (HF:modeling_audio_spectrogram_transformer.py:146-148,197,230,243) and the patch-embedding conv (:88-96).
+#include "zk_b200.h"
+#include "zk_common.cuh"
+#include "zk_internal.cuh"
+
+namespace zk {
+
+namespace gemm {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+struct Params {
+  const float* bias;
+  void* out;
+  const float* aux;
+  long long M;
+  int N, K, aux_rows;
+  int num_m_tiles, num_n_tiles;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// One thread owns 32 consecutive columns [col0, col0+32) of row `row`.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const Params& p, long long row, int col0, const uint32_t (&r)[32]) {
+  if (row >= p.M) return;
+  const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
+  if constexpr (EPI == ZK_EPI_BIAS_BF16 || EPI == ZK_EPI_BIAS_GELU_BF16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.N + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float4 b = __ldg(bias4 + i * 2 + j);
+        v[j * 4 + 0] = __uint_as_float(r[i * 8 + j * 4 + 0]) + b.x;
+        v[j * 4 + 1] = __uint_as_float(r[i * 8 + j * 4 + 1]) + b.y;
+        v[j * 4 + 2] = __uint_as_float(r[i * 8 + j * 4 + 2]) + b.z;
+        v[j * 4 + 3] = __uint_as_float(r[i * 8 + j * 4 + 3]) + b.w;
+      }
+      if constexpr (EPI == ZK_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]);
+      o.w = pack_bf16(v[6], v[7]);
+      dst[i] = o;
+    }
+  } else {
+    long long orow = row;
+    const float4* pos4 = nullptr;
+    if constexpr (EPI == ZK_EPI_PATCH_F32) {
+      long long w = row / p.aux_rows;
+      int pr = (int)(row - w * p.aux_rows);
+      orow = w * (p.aux_rows + 2) + 2 + pr;
+      pos4 = reinterpret_cast<const float4*>(p.aux + (long long)(2 + pr) * p.N + col0);
+    }
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.N + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(bias4 + i);
+      float4 o;
+      if constexpr (EPI == ZK_EPI_PATCH_F32) {
+        o = __ldg(pos4 + i);
+      } else {
+        o = dst[i];
+      }
+      o.x += __uint_as_float(r[i * 4 + 0]) + b.x;
+      o.y += __uint_as_float(r[i * 4 + 1]) + b.y;
+      o.z += __uint_as_float(r[i * 4 + 2]) + b.z;
+      o.w += __uint_as_float(r[i * 4 + 3]) + b.w;
+      dst[i] = o;
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kblocks = p.K / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // which 128 accumulator columns
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + col0, r);
+        tmem_ld_wait();
+        epilogue_store<EPI>(p, row, n_blk * BN + col0, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int EPI>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ZK_LAUNCH_CHECK("gemm_kernel");
+  return 0;
+}
+}  // namespace gemm
+
+int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long long M, int N, int K, int epilogue,
+              const float* aux, int aux_rows, cudaStream_t stream) {
+  using namespace gemm;
+  int rc = device_check();
+  if (rc) return rc;
+  if (!a || !w || !bias || !out || M <= 0) {
+    set_error("gemm_bf16: null pointer or M <= 0");
+    return ZK_ERR_ARG;
+  }
+  if (N % BN || K % BK || N <= 0 || K <= 0) {
+    set_error("gemm_bf16: N (%d) must be a multiple of %d and K (%d) of %d", N, BN, K, BK);
+    return ZK_ERR_SHAPE;
+  }
+  if (epilogue == ZK_EPI_PATCH_F32 && (!aux || aux_rows <= 0)) {
+    set_error("gemm_bf16: ZK_EPI_PATCH_F32 needs the position table and patches per window");
+    return ZK_ERR_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, BK))) return rc;
+  Params p;
+  p.bias = bias;
+  p.out = out;
+  p.aux = aux;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.aux_rows = aux_rows;
+  p.num_m_tiles = (int)((M + BM - 1) / BM);
+  p.num_n_tiles = N / BN;
+  switch (epilogue) {
+    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, p, stream);
+    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, p, stream);
+    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, p, stream);
+    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, p, stream);
+  }
+  set_error("gemm_bf16: unknown epilogue %d", epilogue);
+  return ZK_ERR_ARG;
+}
+
+}  // namespace zk
+
+extern "C" int zk_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int64_t M, int N, int K,
+                            int epilogue, const float* d_aux, int aux_rows, zk_stream_t stream) {
+  return zk::gemm_bf16(d_a, d_w, d_bias, d_out, M, N, K, epilogue, d_aux, aux_rows, (cudaStream_t)stream);
+}

@@ -1,0 +1,108 @@
+// Host-side plumbing of libzk_b200: thread-local error string, device check, TMA tensor maps.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "zk_b200.h"
+#include "zk_common.cuh"
+
+namespace zk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_check = 1;  // 1 = not yet run
+static std::once_flag g_once;
+
+static void do_device_check() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    g_check = cuda_fail(e, "cudaGetDevice");
+    return;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    g_check = cuda_fail(e, "cudaGetDeviceProperties");
+    return;
+  }
+  if (p.major != 10) {
+    set_error("device %s is sm_%d%d; libzk_b200 contains sm_100a code only (no fallback path)", p.name, p.major, p.minor);
+    g_check = ZK_ERR_UNSUPPORTED;
+    return;
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("driver entry point cuTensorMapEncodeTiled not available");
+    g_check = ZK_ERR_UNSUPPORTED;
+    return;
+  }
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  g_check = 0;
+}
+
+int device_check() {
+  std::call_once(g_once, do_device_check);
+  if (g_check != 0 && g_err[0] == 0) set_error("device check failed earlier in this process (code %d)", g_check);
+  return g_check;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  int rc = device_check();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_elems * 2) % 16 || box_cols * 2 != 128 || box_rows > 256) {
+    set_error("make_tmap_bf16_2d: bad alignment/box (base %p pitch %llu box %ux%u)", base,
+              (unsigned long long)pitch_elems, box_rows, box_cols);
+    return ZK_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows %llu cols %llu pitch %llu box %ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, box_rows, box_cols);
+    return ZK_ERR_INTERNAL;
+  }
+  return 0;
+}
+
+}  // namespace zk
+
+extern "C" {
+int zk_abi_version(void) { return ZK_ABI_VERSION; }
+const char* zk_last_error_string(void) { return zk::g_err; }
+int zk_device_check(void) { return zk::device_check(); }
+}

@@ -1,0 +1,364 @@
+// Memory-bound helper kernels of the AST forward and the cascade gate:
+//   layernorm (fp32 residual stream -> bf16 GEMM operand), patch gather (im2col for the 16x16/stride-10 patch
+//   embedding, reading either the (B,1024,128) contract tensor or the compact continuous fbank), cls/dist
+//   token rows, pooled classification head, 2-class softmax, Stage-1 gate + order-preserving compaction.
+#include "zk_b200.h"
+#include "zk_common.cuh"
+#include "zk_internal.cuh"
+
+namespace zk {
+
+// ------------------------------------------------------------------------------------------------ f32 -> bf16
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  }
+  if (i < n) {  // ragged tail (n % 4 != 0), at most one thread
+    for (long long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+  }
+}
+
+int f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+  if (!in || !out || n < 0) {
+    set_error("f32_to_bf16: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) {
+    set_error("f32_to_bf16: pointers must be 16-byte (in) / 8-byte (out) aligned");
+    return ZK_ERR_ARG;
+  }
+  long long groups = (n + 3) / 4;
+  int blocks = (int)((groups + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  f32_to_bf16_kernel<<<blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  ZK_LAUNCH_CHECK("f32_to_bf16_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layernorm
+// One warp per row of 768 fp32 (HF:modeling_audio_spectrogram_transformer.py:260-261,268,275): two-pass
+// mean / biased variance in registers, fp32 math, bf16 result (the A operand of the next GEMM).
+constexpr int LN_COLS = 768;
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps,
+                                                        __nv_bfloat16* __restrict__ out, long long rows) {
+  const int lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row_stride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; row < rows; row += row_stride) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * LN_COLS);
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / LN_COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      v[i].x -= mean;
+      v[i].y -= mean;
+      v[i].z -= mean;
+      v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / LN_COLS) + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + row * LN_COLS);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+      uint2 o;
+      o.x = pack_bf16(v[i].x * rstd * g.x + bb.x, v[i].y * rstd * g.y + bb.y);
+      o.y = pack_bf16(v[i].z * rstd * g.z + bb.z, v[i].w * rstd * g.w + bb.w);
+      orow[lane + 32 * i] = o;
+    }
+  }
+}
+
+int layernorm_bf16(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols,
+                   cudaStream_t stream) {
+  if (!x || !w || !b || !out || rows <= 0) {
+    set_error("layernorm_bf16: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  if (cols != LN_COLS) {
+    set_error("layernorm_bf16: cols must be %d (got %d)", LN_COLS, cols);
+    return ZK_ERR_SHAPE;
+  }
+  long long blocks = (rows + 7) / 8;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  layernorm_kernel<<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
+  ZK_LAUNCH_CHECK("layernorm_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ patch gather
+// A[(b*P + f*nt + t)][kf*16 + kt] = X[b][10 t + kt][10 f + kf]   (P = 12*nt patches per window, nt = (L-16)/10+1)
+// HF:modeling...:92-96: Conv2d over (freq, time) after unsqueeze(1).transpose(2,3); the conv output is
+// flattened frequency-major (patch p = f*nt + t), weight[o][0][kf][kt].
+// One warp per patch; lane = (kf, half of kt): 8 loads along time, one 16-byte store.
+__global__ void __launch_bounds__(256) gather_kernel(GatherSrc src, int batch, int max_length, int nt,
+                                                     __nv_bfloat16* __restrict__ a) {
+  const int lane = threadIdx.x & 31;
+  const int kf = lane >> 1, kt0 = (lane & 1) * 8;
+  const long long patches = (long long)batch * 12 * nt;
+  long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long pstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const float pad = (0.0f - src.mean) / src.std2;
+  for (; p < patches; p += pstride) {
+    const int bwin = (int)(p / (12 * nt));
+    const int rem = (int)(p - (long long)bwin * 12 * nt);
+    const int f = rem / nt, t = rem - f * nt;
+    const int col = 10 * f + kf;
+    float v[8];
+    if (src.features) {
+      const float* xb = src.features + ((long long)bwin * max_length + 10 * t + kt0) * 128 + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(xb + i * 128);
+    } else {
+      const long long w = src.window_index ? (long long)src.window_index[bwin] : (long long)(src.window_base + bwin);
+      const long long frame0 = w * src.frames_per_hop;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tr = 10 * t + kt0 + i;
+        const long long fr = frame0 + tr;
+        float x = pad;
+        if (tr < src.valid_frames && fr < src.fbank_frames) x = (__ldg(src.fbank + fr * 128 + col) - src.mean) / src.std2;
+        v[i] = x;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a + p * 256 + kf * 16 + kt0) = o;
+  }
+}
+
+int gather_patches(const GatherSrc& src, int batch, int max_length, void* a_out, cudaStream_t stream) {
+  const int nt = (max_length - 16) / 10 + 1;
+  long long patches = (long long)batch * 12 * nt;
+  long long blocks = (patches + 7) / 8;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  gather_kernel<<<(int)blocks, 256, 0, stream>>>(src, batch, max_length, nt, reinterpret_cast<__nv_bfloat16*>(a_out));
+  ZK_LAUNCH_CHECK("gather_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ cls / dist rows
+// HF:modeling...:66-69: tokens 0 and 1 of every window are cls_token + pos[0] and distillation_token + pos[1].
+__global__ void special_tokens_kernel(const float* __restrict__ cls, const float* __restrict__ dist,
+                                      const float* __restrict__ pos, float* __restrict__ x, int batch, int tokens) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * 2 * LN_COLS) return;
+  const int bwin = i / (2 * LN_COLS), r = i - bwin * 2 * LN_COLS;
+  const int tok = r / LN_COLS, c = r - tok * LN_COLS;
+  x[((long long)bwin * tokens + tok) * LN_COLS + c] = (tok == 0 ? cls[c] : dist[c]) + pos[tok * LN_COLS + c];
+}
+
+int write_special_tokens(const float* cls, const float* dist, const float* pos, float* x, int batch, int tokens,
+                         cudaStream_t stream) {
+  const int n = batch * 2 * LN_COLS;
+  special_tokens_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cls, dist, pos, x, batch, tokens);
+  ZK_LAUNCH_CHECK("special_tokens_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// HF:modeling...:376-382 (final LayerNorm, only tokens 0 and 1 are consumed), :385-394 (head LayerNorm + dense).
+// One block of 256 threads per window; each thread owns 3 of the 768 channels.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int tokens, const float* __restrict__ fw,
+                                                   const float* __restrict__ fb, const float* __restrict__ hw,
+                                                   const float* __restrict__ hb, const float* __restrict__ dw,
+                                                   const float* __restrict__ db, int num_labels, float eps,
+                                                   float* __restrict__ logits) {
+  __shared__ float red[8];
+  const int bwin = blockIdx.x, tid = threadIdx.x;
+  const float* x0 = x + (long long)bwin * tokens * LN_COLS;
+  float pooled[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pooled[k] = 0.f;
+  for (int tok = 0; tok < 2; ++tok) {
+    float v[3], s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k] = x0[tok * LN_COLS + tid + 256 * k];
+      s += v[k];
+    }
+    const float mean = block_sum_256(s, red) * (1.0f / LN_COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k] -= mean;
+      q += v[k] * v[k];
+    }
+    const float rstd = 1.0f / sqrtf(block_sum_256(q, red) * (1.0f / LN_COLS) + eps);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pooled[k] += v[k] * rstd * fw[tid + 256 * k] + fb[tid + 256 * k];
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    pooled[k] *= 0.5f;
+    s += pooled[k];
+  }
+  const float mean = block_sum_256(s, red) * (1.0f / LN_COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    pooled[k] -= mean;
+    q += pooled[k] * pooled[k];
+  }
+  const float rstd = 1.0f / sqrtf(block_sum_256(q, red) * (1.0f / LN_COLS) + eps);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pooled[k] = pooled[k] * rstd * hw[tid + 256 * k] + hb[tid + 256 * k];
+  for (int c = 0; c < num_labels; ++c) {
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d += pooled[k] * dw[c * LN_COLS + tid + 256 * k];
+    d = block_sum_256(d, red);
+    if (tid == 0) logits[bwin * num_labels + c] = d + db[c];
+  }
+}
+
+int head_logits(const float* x, int batch, int tokens, const float* fln_w, const float* fln_b, const float* hln_w,
+                const float* hln_b, const float* head_w, const float* head_b, int num_labels, float eps, float* logits,
+                cudaStream_t stream) {
+  head_kernel<<<batch, 256, 0, stream>>>(x, tokens, fln_w, fln_b, hln_w, hln_b, head_w, head_b, num_labels, eps, logits);
+  ZK_LAUNCH_CHECK("head_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ gate + compaction
+// ref:111 softmax over 2 classes; ref:312-320 pred = (argmax == 1) & (p1 >= thr) with numpy's first-max tie
+// rule (argmax == 1 iff p1 > p0); refc:471-478 optional extra gate p1 >= min_prob applied to the forwarded set.
+// Order-preserving compaction of the forwarded window indices: warp ballot + popcount prefix inside the warp,
+// a shared-memory scan over the 32 warps, and a running base across the chunks of 1024 windows the single
+// block walks through (a recording has ~1.2e3 .. 1e5 windows: one block is enough and keeps the order exact).
+__device__ __forceinline__ void softmax2(float l0, float l1, float& p0, float& p1) {
+  const float mx = fmaxf(l0, l1);
+  const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+  const float s = e0 + e1;
+  p0 = e0 / s;
+  p1 = e1 / s;
+}
+
+__global__ void __launch_bounds__(1024) gate_compact_kernel(const float* __restrict__ logits, int n, float thr,
+                                                            float min_prob, float* __restrict__ probs,
+                                                            int32_t* __restrict__ pred, int32_t* __restrict__ index,
+                                                            int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + threadIdx.x;
+    bool fwd = false;
+    if (i < n) {
+      float p0, p1;
+      softmax2(logits[2 * i], logits[2 * i + 1], p0, p1);
+      probs[2 * i] = p0;
+      probs[2 * i + 1] = p1;
+      const bool sw = (p1 > p0) && (p1 >= thr);
+      pred[i] = sw ? 1 : 0;
+      fwd = sw && (min_prob < 0.f || p1 >= min_prob);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, fwd);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    {
+      int v = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += y;
+      }
+      off = __shfl_sync(0xffffffffu, v, warp) - warp_tot[warp];  // exclusive prefix of this warp
+      tot = __shfl_sync(0xffffffffu, v, 31);
+    }
+    const int base = base_s;
+    if (fwd) index[base + off + within] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = base + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
+__global__ void softmax2_kernel(const float* __restrict__ logits, int n, float* __restrict__ probs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p0, p1;
+  softmax2(logits[2 * i], logits[2 * i + 1], p0, p1);
+  probs[2 * i] = p0;
+  probs[2 * i + 1] = p1;
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zk_f32_to_bf16(const float* d_in, void* d_out, int64_t n, zk_stream_t stream) {
+  return zk::f32_to_bf16(d_in, d_out, n, (cudaStream_t)stream);
+}
+
+int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows,
+                      int cols, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  return zk::layernorm_bf16(d_x, d_w, d_b, eps, d_out, rows, cols, (cudaStream_t)stream);
+}
+
+int zk_gate_compact(const float* d_logits, int n, float threshold, float min_prob, float* d_probs, int32_t* d_pred,
+                    int32_t* d_index, int32_t* d_count, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (n < 0 || !d_count || (n > 0 && (!d_logits || !d_probs || !d_pred || !d_index))) {
+    zk::set_error("zk_gate_compact: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  zk::gate_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_logits, n, threshold, min_prob, d_probs, d_pred,
+                                                               d_index, d_count);
+  ZK_LAUNCH_CHECK("gate_compact_kernel");
+  return 0;
+}
+
+int zk_softmax2(const float* d_logits, int n, float* d_probs, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!d_logits || !d_probs))) {
+    zk::set_error("zk_softmax2: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  zk::softmax2_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_logits, n, d_probs);
+  ZK_LAUNCH_CHECK("softmax2_kernel");
+  return 0;
+}
+
+}  // extern "C"
