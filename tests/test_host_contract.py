@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's two call contracts (no GPU needed): feature-extractor (de)serialisation,
+argument validation / error behaviour, model directory loading, the transformers swap, sharding and the
+world-size-2 gloo gather."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from zenker_audio_detection_b200 import cascade, compat, dist as zdist, synth
+from zenker_audio_detection_b200.fx import ZenkerASTFeatureExtractor
+from zenker_audio_detection_b200.model import ZenkerASTForAudioClassification
+
+
+def test_fx_roundtrip_and_hf_interop(tmp_path):
+    from transformers import ASTFeatureExtractor
+
+    hf = ASTFeatureExtractor(mean=synth.STAGE1_MEAN, std=synth.STAGE1_STD)
+    hf.save_pretrained(str(tmp_path / "hf"))
+    ours = ZenkerASTFeatureExtractor.from_pretrained(str(tmp_path / "hf"))
+    assert ours.to_dict() == hf.to_dict()
+    assert ours.model_input_names[0] == "input_values"
+    ours.mean, ours.std = -2.0, 4.0
+    ours.save_pretrained(str(tmp_path / "ours"))
+    back = ASTFeatureExtractor.from_pretrained(str(tmp_path / "ours"))
+    assert back.mean == -2.0 and back.std == 4.0 and back.max_length == 1024
+    json.dumps(ours.to_dict(), sort_keys=True)  # refc:84-86 fingerprints this
+    with pytest.raises(OSError):
+        ZenkerASTFeatureExtractor.from_pretrained(str(tmp_path / "missing"))
+
+
+def test_fx_argument_errors_match_hf():
+    fx = ZenkerASTFeatureExtractor()
+    with pytest.raises(ValueError, match="sampling rate"):
+        fx(np.zeros(16000, np.float32), sampling_rate=8000)
+    with pytest.raises(ValueError, match="mono-channel"):
+        fx(np.zeros((2, 3, 100), np.float32), sampling_rate=16000)
+
+
+def test_model_from_pretrained_reads_hf_directory(tmp_path):
+    from safetensors.torch import save_file
+    from transformers import ASTConfig
+
+    sd = synth.random_state_dict(1)
+    root = tmp_path / "m"
+    root.mkdir()
+    ASTConfig(num_labels=2).save_pretrained(str(root))
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(root / "model.safetensors"))
+    cfg = ASTConfig.from_pretrained(str(root))
+    cfg.label2id = {"Idle": 0, "Swallow": 1}
+    cfg.id2label = {0: "Idle", 1: "Swallow"}
+    m = ZenkerASTForAudioClassification.from_pretrained(str(root), config=cfg)
+    assert m.eval() is m and m.num_labels == 2 and m.max_length == 1024 and m.ln_eps == 1e-12
+    assert m.config.id2label[1] == "Swallow"
+    assert len(m.state_dict()) == 203
+    with pytest.raises(ValueError, match="input_values"):
+        m(None)
+    m2 = ZenkerASTForAudioClassification.from_pretrained(str(root))  # config.json read directly
+    assert m2.max_length == 1024
+    bad = ASTConfig(num_labels=2, hidden_size=384)
+    with pytest.raises(Exception):
+        ZenkerASTForAudioClassification(bad, sd)
+
+
+def test_patch_transformers_swaps_the_two_names():
+    import sys
+
+    import transformers  # noqa: F401
+
+    transformers = sys.modules["transformers"]
+    orig = transformers.ASTFeatureExtractor
+    compat.patch_transformers()
+    try:
+        from transformers import ASTConfig, ASTFeatureExtractor, ASTForAudioClassification
+
+        assert ASTFeatureExtractor is ZenkerASTFeatureExtractor
+        assert ASTForAudioClassification is ZenkerASTForAudioClassification
+        assert ASTConfig is transformers.models.audio_spectrogram_transformer.ASTConfig
+    finally:
+        compat.unpatch_transformers()
+    assert transformers.ASTFeatureExtractor is orig
+
+
+def test_shard_recordings_is_balanced_and_deterministic():
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(8 * 60, 12 * 60, size=200).tolist()
+    for ws in (1, 2, 4, 8):
+        shards = zdist.shard_recordings(lengths, ws)
+        assert sorted(i for s in shards for i in s) == list(range(200))
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)
+        assert shards == zdist.shard_recordings(lengths, ws)
+    assert zdist.shard_recordings([5], 4) == [[0], [], [], []]
+
+
+def test_record_pack_unpack_roundtrip():
+    rng = np.random.default_rng(1)
+    s1 = rng.random((37, 2)).astype(np.float32)
+    idx = np.array([0, 5, 6, 30], dtype=np.int64)
+    s2 = rng.random((4, 2)).astype(np.float32)
+    rec = zdist.pack_records(7, s1, idx, s2)
+    rec0 = zdist.pack_records(3, s1[:0], idx[:0], s2[:0])
+    out = zdist.unpack_records(np.concatenate([rec[::-1], rec0]))
+    a, b, c = out[7]
+    assert np.array_equal(a, s1) and np.array_equal(b, idx) and np.array_equal(c, s2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lengths = [1199, 600, 900, 1199, 300]
+    mine = zdist.shard_recordings(lengths, world)[rank]
+    blocks = []
+    for rid in mine:
+        g = np.random.default_rng(100 + rid)  # scores depend on the recording only, never on the rank
+        n = lengths[rid]
+        s1 = g.random((n, 2)).astype(np.float32)
+        idx = np.where(s1[:, 1] > 0.7)[0]
+        s2 = g.random((len(idx), 2)).astype(np.float32)
+        blocks.append(zdist.pack_records(rid, s1, idx, s2))
+    local = np.concatenate(blocks) if blocks else np.zeros((0, zdist.RECORD_WIDTH))
+    allrec = zdist.all_gather_records(local, torch.device("cpu"))
+    per = zdist.unpack_records(allrec)
+    summ = {rid: cascade.summarize_stage_outputs(*per[rid], 0.5) for rid in sorted(per)}
+    q.put((rank, json.dumps(summ, sort_keys=True)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_all_gather_records_gloo(world):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(set(outs.values())) == 1  # every rank reconstructs the identical per-recording summaries
+    # and they equal the single-process result
+    lengths = [1199, 600, 900, 1199, 300]
+    ref = {}
+    for rid, n in enumerate(lengths):
+        g = np.random.default_rng(100 + rid)
+        s1 = g.random((n, 2)).astype(np.float32)
+        idx = np.where(s1[:, 1] > 0.7)[0]
+        s2 = g.random((len(idx), 2)).astype(np.float32)
+        ref[rid] = cascade.summarize_stage_outputs(s1, idx, s2, 0.5)
+    assert json.loads(outs[0]) == json.loads(json.dumps({str(k): v for k, v in ref.items()}, sort_keys=True))
