@@ -182,6 +182,21 @@ int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, floa
 int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream);
 int zk_f32_to_bf16(const float* d_in, void* d_out, int64_t n, zk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Launch accounting (bench.py): every kernel launch of the library is counted per class; with
+ * timing enabled each launch is additionally bracketed by CUDA events on ITS stream.
+ * zk_prof_collect synchronises the device, adds up the event durations and resets the counters.
+ * ------------------------------------------------------------------------------------------ */
+enum zk_kernel_class {
+  ZK_K_RESAMPLE = 0, ZK_K_FBANK = 1, ZK_K_GATHER = 2, ZK_K_GEMM_PATCH = 3, ZK_K_LAYERNORM = 4,
+  ZK_K_GEMM_QKV = 5, ZK_K_ATTENTION = 6, ZK_K_GEMM_OUT = 7, ZK_K_GEMM_FC1 = 8, ZK_K_GEMM_FC2 = 9,
+  ZK_K_HEAD = 10, ZK_K_GATE = 11, ZK_K_MISC = 12, ZK_K_NUM_CLASSES = 13
+};
+void zk_prof_enable(int time_launches);
+/* ms[ZK_K_NUM_CLASSES] (0 where timing was off), launches[ZK_K_NUM_CLASSES]; returns 0 or a cudaError_t */
+int zk_prof_collect(float* ms, int64_t* launches);
+const char* zk_kernel_class_name(int cls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,6 +218,20 @@ def gold_ast():
     print("ast_cfg1", p1[:4], p2[:4], b1, b2)
 
 
+def gold_ast_plain():
+    """HF logits of a PLAIN random init (query/key gain 1, the scale HF's own init has) on 8 cfg1 windows: the
+    1e-2 bf16 logit tolerance of north_star is checked on this one; the sensitised models above amplify bf16 noise."""
+    w = synth.cfg1_windows(64)[:8]
+    fx1 = T.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
+    sd = synth.random_state_dict(33, qk_gain=1.0)
+    m = T.hf_model_from_state_dict(sd)
+    with torch.inference_mode():
+        f = fx1(list(w), sampling_rate=16000, return_tensors="pt")["input_values"]
+        l = m(f).logits.numpy()
+    np.savez_compressed(os.path.join(GOLD, "ast_plain.npz"), logits=l, seed=33, qk_gain=1.0)
+    print("ast_plain", l[:3])
+
+
 def gold_cascade_60s():
     g = np.load(os.path.join(GOLD, "ast_cfg1.npz"))
     fx1 = T.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
@@ -252,7 +266,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "ast", "cascade60"]
+    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "ast", "astplain", "cascade60"]
     if "windows" in todo:
         gold_windows()
     if "cascade" in todo:
@@ -264,5 +278,7 @@ if __name__ == "__main__":
     if not a.skip_ast:
         if "ast" in todo:
             gold_ast()
+        if "astplain" in todo:
+            gold_ast_plain()
         if "cascade60" in todo:
             gold_cascade_60s()

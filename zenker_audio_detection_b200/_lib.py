@@ -76,7 +76,24 @@ SIGNATURES = {
                                     C.c_void_p]),
     "zk_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "zk_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "zk_prof_enable": (None, [C.c_int]),
+    "zk_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zk_kernel_class_name": (C.c_char_p, [C.c_int]),
 }
+NUM_KERNEL_CLASSES = 13
+
+
+def prof_enable(time_launches: bool) -> None:
+    load().zk_prof_enable(1 if time_launches else 0)
+
+
+def prof_collect():
+    """-> {class name: (ms, launches)}; synchronises the device and resets the counters."""
+    lib = load()
+    ms = (C.c_float * NUM_KERNEL_CLASSES)()
+    n = (C.c_int64 * NUM_KERNEL_CLASSES)()
+    check(lib.zk_prof_collect(ms, n), "zk_prof_collect")
+    return {lib.zk_kernel_class_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(NUM_KERNEL_CLASSES)}
 
 _lib: Optional[C.CDLL] = None
 

@@ -240,6 +240,7 @@ int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
   dim3 grid((tokens + BQ - 1) / BQ, HEADS, batch);
+  ProfScope prof(ZK_K_ATTENTION, stream);
   attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;

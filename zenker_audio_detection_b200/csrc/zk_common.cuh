@@ -185,6 +185,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ----------------------------------------------------------------------------- launch accounting
+struct ProfScope {  // counts one launch of class `cls`; brackets it with events when timing is enabled
+  ProfScope(int cls, cudaStream_t stream);
+  ~ProfScope();
+  int cls_;
+  cudaStream_t stream_;
+  void* stop_;
+};
+
 // ----------------------------------------------------------------------------- host helpers
 int device_check();  // 0 when the device is sm_100 and the tensor-map encoder is available
 int num_sms();

@@ -191,6 +191,7 @@ static int launch_fbank(const zk_fbank_plan* plan, Job job, cudaStream_t stream)
   if (job.num_tiles <= 0) return 0;
   const bool bulk = (reinterpret_cast<uintptr_t>(job.wave) % 16 == 0) && (job.src_pitch % 4 == 0);
   long long grid = job.num_tiles < 2LL * num_sms() ? job.num_tiles : 2LL * num_sms();
+  ProfScope prof(ZK_K_FBANK, stream);
   if (bulk)
     fbank_kernel<true><<<(int)grid, THREADS, SMEM_BYTES, stream>>>(*plan, job);
   else
@@ -301,6 +302,7 @@ static int run(const T* in, long long n_in, int channels, long long ch_pitch, co
   if (new_ == 1 && orig == O && width == W) {                                                                 \
     long long blocks = (n_out + 128 * R - 1) / (128 * R);                                                      \
     if (blocks > 8LL * sms) blocks = 8LL * sms;                                                                \
+    ProfScope prof(ZK_K_RESAMPLE, stream);                                                                     \
     decimate_kernel<T, O, W, R><<<(int)blocks, 128, 0, stream>>>(in, n_in, channels, ch_pitch, taps, out, n_out); \
     ZK_LAUNCH_CHECK("decimate_kernel");                                                                       \
     return 0;                                                                                                 \
@@ -311,6 +313,7 @@ static int run(const T* in, long long n_in, int channels, long long ch_pitch, co
 #undef ZK_DECIMATE
   long long blocks = (n_out + 255) / 256;
   if (blocks > 16LL * sms) blocks = 16LL * sms;
+  ProfScope prof(ZK_K_RESAMPLE, stream);
   generic_kernel<T><<<(int)blocks, 256, 0, stream>>>(in, n_in, channels, ch_pitch, taps, orig, new_, width, out, n_out);
   ZK_LAUNCH_CHECK("resample generic_kernel");
   return 0;
@@ -438,6 +441,7 @@ int zk_fx_contract_f32(const zk_fbank_plan* plan, const float* d_windows, int ba
     long long total = (long long)batch * (max_length - rows) * (NMEL / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 8LL * zk::num_sms()) blocks = 8LL * zk::num_sms();
+    zk::ProfScope prof(ZK_K_MISC, (cudaStream_t)stream);
     fill_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, batch, rows, max_length, pad);
     ZK_LAUNCH_CHECK("fill_pad_kernel");
   }

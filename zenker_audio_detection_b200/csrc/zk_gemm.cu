@@ -206,7 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int EPI>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int prof_cls, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     ZK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -214,6 +214,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope prof(prof_cls, stream);
   gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
   ZK_LAUNCH_CHECK("gemm_kernel");
   return 0;
@@ -251,10 +252,10 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
   switch (epilogue) {
-    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, p, stream);
-    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, p, stream);
-    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, p, stream);
-    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, p, stream);
+    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, p, ZK_K_GEMM_QKV, stream);
+    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, p, ZK_K_GEMM_FC1, stream);
+    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, p, K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT, stream);
+    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, p, ZK_K_GEMM_PATCH, stream);
   }
   set_error("gemm_bf16: unknown epilogue %d", epilogue);
   return ZK_ERR_ARG;

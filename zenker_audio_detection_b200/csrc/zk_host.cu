@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "zk_b200.h"
 #include "zk_common.cuh"
@@ -99,9 +100,76 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- profiler
+struct ProfRec {
+  int cls;
+  cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_time = false;
+static long long g_prof_count[ZK_K_NUM_CLASSES] = {0};
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int cls, cudaStream_t stream) : cls_(cls), stream_(stream), stop_(nullptr) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_count[cls]++;
+  if (!g_prof_time) return;
+  ProfRec r{cls, prof_event(), prof_event()};
+  if (!r.a || !r.b) return;
+  cudaEventRecord(r.a, stream);
+  stop_ = r.b;
+  g_prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (stop_) cudaEventRecord((cudaEvent_t)stop_, stream_);
+}
+
 }  // namespace zk
 
 extern "C" {
+void zk_prof_enable(int time_launches) {
+  std::lock_guard<std::mutex> lk(zk::g_prof_mu);
+  zk::g_prof_time = time_launches != 0;
+}
+
+int zk_prof_collect(float* ms, int64_t* launches) {
+  cudaError_t e = cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(zk::g_prof_mu);
+  for (int i = 0; i < ZK_K_NUM_CLASSES; ++i) {
+    if (ms) ms[i] = 0.f;
+    if (launches) launches[i] = zk::g_prof_count[i];
+    zk::g_prof_count[i] = 0;
+  }
+  for (auto& r : zk::g_prof_recs) {
+    float t = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && ms) ms[r.cls] += t;
+    zk::g_prof_pool.push_back(r.a);
+    zk::g_prof_pool.push_back(r.b);
+  }
+  zk::g_prof_recs.clear();
+  if (e != cudaSuccess) return zk::cuda_fail(e, "zk_prof_collect");
+  return 0;
+}
+
+const char* zk_kernel_class_name(int cls) {
+  static const char* names[ZK_K_NUM_CLASSES] = {"resample", "fbank", "gather_patches", "gemm_patch", "layernorm",
+                                               "gemm_qkv", "attention", "gemm_out", "gemm_fc1", "gemm_fc2",
+                                               "head", "gate", "misc"};
+  return (cls >= 0 && cls < ZK_K_NUM_CLASSES) ? names[cls] : "?";
+}
+
 int zk_abi_version(void) { return ZK_ABI_VERSION; }
 const char* zk_last_error_string(void) { return zk::g_err; }
 int zk_device_check(void) { return zk::device_check(); }

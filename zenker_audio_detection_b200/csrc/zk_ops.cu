@@ -37,6 +37,7 @@ int f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
   long long groups = (n + 3) / 4;
   int blocks = (int)((groups + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ProfScope prof(ZK_K_MISC, stream);
   f32_to_bf16_kernel<<<blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
   ZK_LAUNCH_CHECK("f32_to_bf16_kernel");
   return 0;
@@ -97,6 +98,7 @@ int layernorm_bf16(const float* x, const float* w, const float* b, float eps, vo
   }
   long long blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  ProfScope prof(ZK_K_LAYERNORM, stream);
   layernorm_kernel<<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
   ZK_LAUNCH_CHECK("layernorm_kernel");
   return 0;
@@ -151,6 +153,7 @@ int gather_patches(const GatherSrc& src, int batch, int max_length, void* a_out,
   long long patches = (long long)batch * 12 * nt;
   long long blocks = (patches + 7) / 8;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ProfScope prof(ZK_K_GATHER, stream);
   gather_kernel<<<(int)blocks, 256, 0, stream>>>(src, batch, max_length, nt, reinterpret_cast<__nv_bfloat16*>(a_out));
   ZK_LAUNCH_CHECK("gather_kernel");
   return 0;
@@ -170,6 +173,7 @@ __global__ void special_tokens_kernel(const float* __restrict__ cls, const float
 int write_special_tokens(const float* cls, const float* dist, const float* pos, float* x, int batch, int tokens,
                          cudaStream_t stream) {
   const int n = batch * 2 * LN_COLS;
+  ProfScope prof(ZK_K_MISC, stream);
   special_tokens_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cls, dist, pos, x, batch, tokens);
   ZK_LAUNCH_CHECK("special_tokens_kernel");
   return 0;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
 int head_logits(const float* x, int batch, int tokens, const float* fln_w, const float* fln_b, const float* hln_w,
                 const float* hln_b, const float* head_w, const float* head_b, int num_labels, float eps, float* logits,
                 cudaStream_t stream) {
+  ProfScope prof(ZK_K_HEAD, stream);
   head_kernel<<<batch, 256, 0, stream>>>(x, tokens, fln_w, fln_b, hln_w, hln_b, head_w, head_b, num_labels, eps, logits);
   ZK_LAUNCH_CHECK("head_kernel");
   return 0;
@@ -342,6 +347,7 @@ int zk_gate_compact(const float* d_logits, int n, float threshold, float min_pro
     zk::set_error("zk_gate_compact: bad arguments");
     return ZK_ERR_ARG;
   }
+  zk::ProfScope prof(ZK_K_GATE, (cudaStream_t)stream);
   zk::gate_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_logits, n, threshold, min_prob, d_probs, d_pred,
                                                                d_index, d_count);
   ZK_LAUNCH_CHECK("gate_compact_kernel");
@@ -356,6 +362,7 @@ int zk_softmax2(const float* d_logits, int n, float* d_probs, zk_stream_t stream
     return ZK_ERR_ARG;
   }
   if (n == 0) return 0;
+  zk::ProfScope prof(ZK_K_GATE, (cudaStream_t)stream);
   zk::softmax2_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_logits, n, d_probs);
   ZK_LAUNCH_CHECK("softmax2_kernel");
   return 0;
