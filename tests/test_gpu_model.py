@@ -31,7 +31,7 @@ def test_one_layer_hidden_state():
     ref_logits, ref_hidden = _oracle_logits(sd, feats, num_layers=1, return_hidden=True)
     diff = (hidden - ref_hidden)
     rel = (diff.norm() / ref_hidden.norm()).item()
-    assert rel <= 4e-3, rel                      # bf16 operands, fp32 accumulation / residual stream
+    assert rel <= 1.2e-2, rel                    # bf16 operands (2^-9 each), fp32 accumulation / residual stream
     assert diff.abs().max().item() <= 8e-2       # max over 3.7 M elements
     assert (hidden[:, :2] - ref_hidden[:, :2]).abs().max().item() <= 3e-2  # cls / dist tokens
     assert (logits - ref_logits).abs().max().item() <= 1e-2
