@@ -5,9 +5,11 @@
 //   warp 0      TMA producer: Q tile once, then a 2-stage ring of {K_j, V_j} 128x64 bf16 tiles
 //   warp 1      TMEM allocator + MMA issuer:  S = Q K_j^T (UMMA 128x128x16, TMEM cols [0,128)),
 //               O_j = P_j V_j (UMMA 128x64x16, V as MN-major operand, TMEM cols 128 + 64*(j&1))
-//   warps 2..5  softmax: one query row per thread, fp32 online softmax straight out of TMEM, P_j written
-//               to 128B-swizzled shared memory as the bf16 A operand of the second MMA; the running output
-//               is kept in registers and rescaled there (no TMEM read-modify-write).
+//   warps 2..5  softmax: one query row per thread; the whole 128-wide S row is pulled out of TMEM in one burst,
+//               fp32 max (FMNMX3) / exp2 (FFMA2 + MUFU) / sum (FADD2), P_j written to 128B-swizzled shared
+//               memory as the bf16 A operand of the second MMA.  O accumulates in TMEM across key blocks;
+//               the running maximum is only advanced (and O rescaled in TMEM, a rare tcgen05.ld/st round
+//               trip) when a block maximum exceeds it by more than 2^8, so the common path never touches O.
 //
 // Q, K and V are read in place from the fused QKV projection output [batch*tokens][2304] (q | k | v, head h
 // at columns 64h), keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
@@ -26,6 +28,7 @@ constexpr int OFF_Q = 0, OFF_KV = TILE_BYTES, OFF_P = OFF_KV + KV_STAGES * 2 * T
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256, TM_S = 0, TM_O = 128;
+constexpr float RESCALE_TAU = 8.0f;  // in log2 units: p <= 2^8 with a stale maximum
 constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
 constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V) is MN-major
 constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
@@ -39,7 +42,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
   uint64_t* kv_empty = bars + 3;  // [2]
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;  // [2]
+  uint64_t* pv_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -57,8 +60,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-      mbar_init(&o_full[i], 1);
     }
+    mbar_init(pv_done, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     fence_barrier_init();
@@ -103,15 +106,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
         if (j + 1 < nkv) issue_s(j + 1);
         const int st = j & 1;
         const uint32_t sv = smem_u32(smem + OFF_KV + st * 2 * TILE_BYTES + TILE_BYTES);
-        const uint32_t d_o = tmem_base + TM_O + (j & 1) * D;
+        const uint32_t d_o = tmem_base + TM_O;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P: two 64-key swizzle atoms of 16 KiB; B = V_j: 16 keys = 16 rows of 128 B (MN-major)
           const uint64_t p_desc = umma_desc_sw128(sp + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
           const uint64_t v_desc = umma_desc_sw128(sv + k * 16 * 128, 1024, 1024);
-          umma_bf16_ss(d_o, p_desc, v_desc, IDESC_O, k != 0);
+          umma_bf16_ss(d_o, p_desc, v_desc, IDESC_O, (j | k) != 0);
         }
-        umma_commit(&o_full[j & 1]);
+        umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
       }
     }
@@ -120,58 +123,86 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sp_row = smem_u32(smem + OFF_P) + row * 128;
-    float m = -INFINITY, l = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float m = -INFINITY;
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_lane + TM_S + c * 32, r);
-        tmem_ld_wait();
+      const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
+      const bool ragged = kmax < BKV;
+      uint32_t buf[2][32];
+      // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      tmem_ld32(t_lane + TM_S, buf[0]);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if (c * 32 + i >= kmax) s = -INFINITY;
-          mx = fmaxf(mx, s);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t(&cur)[32] = buf[c & 1];
+        if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kmax) cur[i] = 0xff800000u;  // -inf
         }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(cur[i + 0]), __uint_as_float(cur[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
+        }
+        if (c < 3) tmem_ld_wait();
       }
-      const float alpha = fast_exp2((m - mx) * SCALE_LOG2E);
-      if (j > 0) {  // fold in O_{j-1} = P_{j-1} V_{j-1} (relative to the old maximum), then rescale
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      tmem_ld32(t_lane + TM_S, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
+      bool waited_pv = false;
+      if (j == 0) {
+        m = mx;
+      } else if (__any_sync(0xffffffffu, (mx - m) * SCALE_LOG2E > RESCALE_TAU)) {
+        // rare: advance the running maximum and rescale the accumulator in TMEM (whole warp, tcgen05 is collective)
+        const float mn = fmaxf(m, mx);
+        const float alpha = fast_exp2((m - mn) * SCALE_LOG2E);
+        m = mn;
+        l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
+        mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
+        waited_pv = true;
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_lane + TM_O + ((j - 1) & 1) * D + c * 32, r);
+          tmem_ld32(t_lane + TM_O + c * 32, buf[1]);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+          for (int i = 0; i < 32; ++i) buf[1][i] = __float_as_uint(__uint_as_float(buf[1][i]) * alpha);
+          tmem_st32(t_lane + TM_O + c * 32, buf[1]);
         }
+        tmem_st_wait();
       }
-      l *= alpha;
-      m = mx;
-      const float mb = mx * SCALE_LOG2E;
-#pragma unroll 1
+      // ---- pass 2: p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of the A operand of P V
+      const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
+      const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
+      tmem_ld_wait();
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_lane + TM_S + c * 32, r);
-        tmem_ld_wait();
+        uint32_t(&cur)[32] = buf[c & 1];
+        if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kmax) cur[i] = 0xff800000u;
+        }
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -mb));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), SCALE_LOG2E, -mb));
-          if (c * 32 + i >= kmax) p0 = 0.f;
-          if (c * 32 + i + 1 >= kmax) p1 = 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+        for (int i = 0; i < 32; i += 4) {
+          const float2 xa = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, mb2);
+          const float2 xb = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, mb2);
+          const float2 pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+          const float2 pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+          l2a = fadd2(l2a, pa);
+          l2b = fadd2(l2b, pb);
+          pk[i >> 1] = pack_bf16(pa.x, pa.y);
+          pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
         }
         // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
         const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
@@ -180,6 +211,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
           const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
           st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
+        if (c < 3) tmem_ld_wait();
       }
       tc_fence_before();
       fence_proxy_async();
@@ -187,26 +219,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
     }
     {
       const int jl = nkv - 1;
-      mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
+      mbar_wait(pv_done, jl & 1);
       tc_fence_after();
-      const float inv = 1.0f / l;
+      const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
       const int q = qb * BQ + row;
       __nv_bfloat16* dst = out + (long long)(row_base + q) * HID + h * D;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(t_lane + TM_O + (jl & 1) * D + c * 32, r);
+        tmem_ld32(t_lane + TM_O + c * 32, r);
         tmem_ld_wait();
         if (q < tokens) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 v;
-            const int i0 = c * 32 + g * 8;
-            v.x = pack_bf16((o[i0 + 0] + __uint_as_float(r[g * 8 + 0])) * inv, (o[i0 + 1] + __uint_as_float(r[g * 8 + 1])) * inv);
-            v.y = pack_bf16((o[i0 + 2] + __uint_as_float(r[g * 8 + 2])) * inv, (o[i0 + 3] + __uint_as_float(r[g * 8 + 3])) * inv);
-            v.z = pack_bf16((o[i0 + 4] + __uint_as_float(r[g * 8 + 4])) * inv, (o[i0 + 5] + __uint_as_float(r[g * 8 + 5])) * inv);
-            v.w = pack_bf16((o[i0 + 6] + __uint_as_float(r[g * 8 + 6])) * inv, (o[i0 + 7] + __uint_as_float(r[g * 8 + 7])) * inv);
-            *reinterpret_cast<uint4*>(dst + i0) = v;
+            v.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = v;
           }
         }
       }

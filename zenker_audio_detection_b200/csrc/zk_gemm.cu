@@ -3,7 +3,9 @@
 //
 //   warp 0      TMA producer   (4-stage ring of {A 128x64, W 256x64} bf16 tiles, 48 KiB / stage)
 //   warp 1      TMEM allocator + MMA issuer (UMMA 128x256x16, 4 per stage)
-//   warps 2..9  epilogue: TMEM -> registers -> fused bias / GELU / residual / position-embedding -> global
+//   warps 2..9  epilogue: TMEM -> registers -> fused bias / GELU -> 128B-swizzled smem staging -> TMA tile store
+//               (bf16 outputs) or TMA tile REDUCE-ADD into the fp32 residual stream (x += acc + bias without the
+//               SMs ever reading x); the patch-embedding variant scatters rows directly (+position table)
 //
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
 // MMAs of tile t+1.  Replaces the cuBLAS calls behind nn.Linear on the reference path
@@ -19,7 +21,10 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int STG_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 128 B (64 bf16 / 32 fp32 columns)
+constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
 
 struct Params {
@@ -31,71 +36,72 @@ struct Params {
   int num_m_tiles, num_n_tiles;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (HF "gelu") from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): two MUFU ops (rcp, ex2) and
+// ~12 FMA-pipe ops per element instead of erff()'s branchy ~30, so the fc1 epilogue stays hidden under the MMAs.
+//   z = |x|/sqrt2, t = 1/(1 + p z), q = x/2 * (a1 t + .. + a5 t^5) * exp(-z^2);  gelu(x) = x >= 0 ? x - q : q
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = fast_exp2(x * x * (-0.5f * 1.44269504088896340736f));
+  const float q = 0.5f * x * poly * e;
+  return x >= 0.f ? x - q : q;
+}
 
-// One thread owns 32 consecutive columns [col0, col0+32) of row `row`.
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const Params& p, long long row, int col0, const uint32_t (&r)[32]) {
+// PATCH epilogue only: one thread owns 32 consecutive columns [col0, col0+32) of row `row`; rows are scattered to
+// token rows 2.. of their window and the position table is added (0.2 % of the FLOPs, direct stores are fine).
+__device__ __forceinline__ void patch_store(const Params& p, long long row, int col0, const uint32_t (&r)[32]) {
   if (row >= p.M) return;
   const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
-  if constexpr (EPI == ZK_EPI_BIAS_BF16 || EPI == ZK_EPI_BIAS_GELU_BF16) {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.N + col0);
+  const long long w = row / p.aux_rows;
+  const int pr = (int)(row - w * p.aux_rows);
+  const long long orow = w * (p.aux_rows + 2) + 2 + pr;
+  const float4* pos4 = reinterpret_cast<const float4*>(p.aux + (long long)(2 + pr) * p.N + col0);
+  float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.N + col0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v[8];
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(bias4 + i);
+    float4 o = __ldg(pos4 + i);
+    o.x += __uint_as_float(r[i * 4 + 0]) + b.x;
+    o.y += __uint_as_float(r[i * 4 + 1]) + b.y;
+    o.z += __uint_as_float(r[i * 4 + 2]) + b.z;
+    o.w += __uint_as_float(r[i * 4 + 3]) + b.w;
+    dst[i] = o;
+  }
+}
+
+// 32 accumulator columns (+bias, optional GELU) -> 16 packed bf16 pairs
+template <bool GELU>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&r)[32], const float* bias, uint32_t (&pk)[16]) {
+  const float4* bias4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float4 b = __ldg(bias4 + i * 2 + j);
-        v[j * 4 + 0] = __uint_as_float(r[i * 8 + j * 4 + 0]) + b.x;
-        v[j * 4 + 1] = __uint_as_float(r[i * 8 + j * 4 + 1]) + b.y;
-        v[j * 4 + 2] = __uint_as_float(r[i * 8 + j * 4 + 2]) + b.z;
-        v[j * 4 + 3] = __uint_as_float(r[i * 8 + j * 4 + 3]) + b.w;
-      }
-      if constexpr (EPI == ZK_EPI_BIAS_GELU_BF16) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-      }
-      uint4 o;
-      o.x = pack_bf16(v[0], v[1]);
-      o.y = pack_bf16(v[2], v[3]);
-      o.z = pack_bf16(v[4], v[5]);
-      o.w = pack_bf16(v[6], v[7]);
-      dst[i] = o;
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(bias4 + i);
+    float v0 = __uint_as_float(r[i * 4 + 0]) + b.x, v1 = __uint_as_float(r[i * 4 + 1]) + b.y;
+    float v2 = __uint_as_float(r[i * 4 + 2]) + b.z, v3 = __uint_as_float(r[i * 4 + 3]) + b.w;
+    if (GELU) {
+      v0 = gelu_erf(v0);
+      v1 = gelu_erf(v1);
+      v2 = gelu_erf(v2);
+      v3 = gelu_erf(v3);
     }
-  } else {
-    long long orow = row;
-    const float4* pos4 = nullptr;
-    if constexpr (EPI == ZK_EPI_PATCH_F32) {
-      long long w = row / p.aux_rows;
-      int pr = (int)(row - w * p.aux_rows);
-      orow = w * (p.aux_rows + 2) + 2 + pr;
-      pos4 = reinterpret_cast<const float4*>(p.aux + (long long)(2 + pr) * p.N + col0);
-    }
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.N + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(bias4 + i);
-      float4 o;
-      if constexpr (EPI == ZK_EPI_PATCH_F32) {
-        o = __ldg(pos4 + i);
-      } else {
-        o = dst[i];
-      }
-      o.x += __uint_as_float(r[i * 4 + 0]) + b.x;
-      o.y += __uint_as_float(r[i * 4 + 1]) + b.y;
-      o.z += __uint_as_float(r[i * 4 + 2]) + b.z;
-      o.w += __uint_as_float(r[i * 4 + 3]) + b.w;
-      dst[i] = o;
-    }
+    pk[i * 2 + 0] = pack_bf16(v0, v1);
+    pk[i * 2 + 1] = pack_bf16(v2, v3);
   }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -107,6 +113,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != ZK_EPI_PATCH_F32) tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -178,6 +185,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;     // which 128 accumulator columns
+    uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES;  // this warp's 32 x 128 B staging tile (1024-B aligned)
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
@@ -185,19 +194,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc_phase = (t >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const long long row = (long long)m_blk * BM + quarter * 32 + lane;
+      const int row0 = m_blk * BM + quarter * 32;
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      const int col_base = n_blk * BN + half * 128;
+      if constexpr (EPI == ZK_EPI_PATCH_F32) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = half * 128 + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + col0, r);
-        tmem_ld_wait();
-        epilogue_store<EPI>(p, row, n_blk * BN + col0, r);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_ld_wait();
+          patch_store(p, (long long)row0 + lane, col_base + c * 32, r);
+        }
+      } else if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
+        // 4 chunks of 32 fp32 columns: (acc + bias) -> staging -> TMA reduce-add into the residual stream
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_ld_wait();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+          if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + i);
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, stg, col_base + c * 32, row0);
+            bulk_commit();
+          }
+        }
+      } else {
+        // 2 chunks of 64 bf16 columns: (acc + bias [, GELU]) -> staging -> TMA store
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_acc + c * 64, r0);
+          tmem_ld32(t_acc + c * 64 + 32, r1);
+          tmem_ld_wait();
+          uint32_t pk[32];
+          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r0, p.bias + col_base + c * 64,
+                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r1, p.bias + col_base + c * 64 + 32,
+                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), pk[i * 4 + 0], pk[i * 4 + 1], pk[i * 4 + 2],
+                         pk[i * 4 + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, col_base + c * 64, row0);
+            bulk_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (lane == 0) bulk_wait0();  // all tile stores of this warp have landed before the CTA retires
   }
   __syncwarp();
   tc_fence_before();
@@ -206,7 +270,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int EPI>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int prof_cls, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
+                  cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     ZK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -215,7 +280,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope prof(prof_cls, stream);
-  gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }
@@ -238,9 +303,16 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
     set_error("gemm_bf16: ZK_EPI_PATCH_F32 needs the position table and patches per window");
     return ZK_ERR_ARG;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   if ((rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, BK))) return rc;
+  if (epilogue == ZK_EPI_BIAS_BF16 || epilogue == ZK_EPI_BIAS_GELU_BF16) {
+    if ((rc = make_tmap_bf16_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64))) return rc;
+  } else if (epilogue == ZK_EPI_BIAS_RESID_F32) {
+    if ((rc = make_tmap_f32_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32))) return rc;
+  } else {
+    tmC = tmA;  // unused by the patch epilogue
+  }
   Params p;
   p.bias = bias;
   p.out = out;
@@ -252,10 +324,10 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
   switch (epilogue) {
-    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, p, ZK_K_GEMM_QKV, stream);
-    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, p, ZK_K_GEMM_FC1, stream);
-    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, p, K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT, stream);
-    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, p, ZK_K_GEMM_PATCH, stream);
+    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, ZK_K_GEMM_QKV, stream);
+    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, ZK_K_GEMM_FC1, stream);
+    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT, stream);
+    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, tmC, p, ZK_K_GEMM_PATCH, stream);
   }
   set_error("gemm_bf16: unknown epilogue %d", epilogue);
   return ZK_ERR_ARG;

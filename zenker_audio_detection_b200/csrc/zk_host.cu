@@ -76,28 +76,36 @@ int num_sms() {
   return n;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+static int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, uint32_t esize, const void* base, uint64_t rows,
+                        uint64_t cols, uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
   int rc = device_check();
   if (rc) return rc;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_elems * 2) % 16 || box_cols * 2 != 128 || box_rows > 256) {
-    set_error("make_tmap_bf16_2d: bad alignment/box (base %p pitch %llu box %ux%u)", base,
-              (unsigned long long)pitch_elems, box_rows, box_cols);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_elems * esize) % 16 || box_cols * esize != 128 || box_rows > 256) {
+    set_error("make_tmap_2d: bad alignment/box (base %p pitch %llu box %ux%u esize %u)", base,
+              (unsigned long long)pitch_elems, box_rows, box_cols, esize);
     return ZK_ERR_ARG;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {pitch_elems * 2};
+  cuuint64_t gstr[1] = {pitch_elems * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows %llu cols %llu pitch %llu box %ux%u", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, box_rows, box_cols);
     return ZK_ERR_INTERNAL;
   }
   return 0;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, pitch_elems, box_rows, box_cols);
+}
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                     uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, pitch_elems, box_rows, box_cols);
 }
 
 // ---------------------------------------------------------------------------------------------- profiler
