@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Per-kernel timings on a B200 (CUDA events, L2 flushed by working sets >> 126 MB): tcgen05 GEMMs at the AST
+shapes, fused attention, layernorm, fbank (cfg3: 1 h @ 16 kHz) and resampler (cfg2: 10 min @ 48 kHz)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zenker_audio_detection_b200 import _lib, ops, synth  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    B = int(os.environ.get("ZK_BENCH_BATCH", "128"))
+    T = 1214
+    M = B * T
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(M, 768, device="cuda", generator=g)
+    a768 = (torch.randn(M, 768, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    a3072 = (torch.randn(M, 3072, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    for name, a, N, K, epi in (("gemm_qkv", a768, 2304, 768, _lib.EPI_BIAS_BF16), ("gemm_fc1", a768, 3072, 768, _lib.EPI_BIAS_GELU_BF16),
+                               ("gemm_out", a768, 768, 768, _lib.EPI_BIAS_RESID_F32), ("gemm_fc2", a3072, 768, 3072, _lib.EPI_BIAS_RESID_F32)):
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda", generator=g) * 0.1
+        o = x if epi == _lib.EPI_BIAS_RESID_F32 else torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.gemm(a, w, b, epi, out=o))
+        tf = 2.0 * M * N * K / ms / 1e9
+        out[name] = {"ms": ms, "tflops": tf, "frac_burst": tf / PEAKS["bf16_tflops"], "frac_sustained": tf / PEAKS["bf16_tflops_sustained"]}
+        ref = timeit(lambda: torch.matmul(a, w.t()))
+        out[name]["cublas_ms"] = ref
+        del w, o
+    qkv = (torch.randn(M, 2304, device="cuda", generator=g)).to(torch.bfloat16)
+    qkv[:, :1536] *= 2.0
+    ms = timeit(lambda: ops.attention(qkv, B, T))
+    tf = 4.0 * B * 12 * T * T * 64 / ms / 1e9
+    out["attention"] = {"ms": ms, "tflops": tf, "frac_sustained": tf / PEAKS["bf16_tflops_sustained"], "poly": os.environ.get("ZK_ATTN_POLY", "default")}
+    # accuracy of the attention variant on a small case
+    q2 = qkv[: 2 * T].clone()
+    got = ops.attention(q2, 2, T).float()
+    q, k, v = (q2[:, i * 768:(i + 1) * 768].float().view(2, T, 12, 64).transpose(1, 2) for i in range(3))
+    ref = (torch.softmax((q @ k.transpose(2, 3)) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(2 * T, 768)
+    out["attention"]["max_abs_err"] = (got - ref).abs().max().item()
+    out["attention"]["rel_err"] = ((got - ref).norm() / ref.norm()).item()
+    sd = ms_sdpa = None
+    try:
+        qq, kk, vv = (qkv[:, i * 768:(i + 1) * 768].view(B, T, 12, 64).transpose(1, 2) for i in range(3))
+        ms_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv))
+    except Exception as e:  # noqa: BLE001
+        sd = str(e)
+    out["attention"]["torch_sdpa_ms"] = ms_sdpa
+    del qkv
+    w = torch.ones(768, device="cuda")
+    ms = timeit(lambda: ops.layernorm(x, w, w, 1e-12))
+    out["layernorm"] = {"ms": ms, "gbs": M * 768 * 6 / ms / 1e6, "frac_hbm": M * 768 * 6 / ms / 1e6 / PEAKS["hbm_gbs"]}
+    del x, a768, a3072
+    # fbank cfg3: 1 h @ 16 kHz in one launch (algorithmic bytes 4 n + 512 m); repeat on 4 h to amortise launch overhead
+    plan = ops.FbankPlan()
+    for hours in (1, 4):
+        n = hours * 57_600_000
+        wave = torch.randn(n, device="cuda", generator=g) * 0.05
+        m = plan.num_frames(n)
+        ms = timeit(lambda: plan.fbank(wave), iters=5, warm=2)
+        by = 4.0 * n + 512.0 * m
+        out[f"fbank_{hours}h"] = {"ms": ms, "gbs": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / PEAKS["hbm_gbs"], "frames": m}
+        del wave
+    rec = torch.randn(28_800_000, device="cuda", generator=g) * 0.1
+    ms = timeit(lambda: ops.resample(rec, 48000, 16000))
+    by = 4.0 * 28_800_000 + 4.0 * 9_600_000
+    out["resample_cfg2"] = {"ms": ms, "gbs": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / PEAKS["hbm_gbs"]}
+    wins = torch.randn(1024, 16000, device="cuda", generator=g) * 0.05
+    ms = timeit(lambda: plan.fx_contract(wins, -1.15, 3.53, 1024))
+    by = 1024 * 588288.0
+    out["fx_contract_1024win"] = {"ms": ms, "gbs": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / PEAKS["hbm_gbs"], "windows_per_s": 1024 / ms * 1e3}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,8 @@
 // Q, K and V are read in place from the fused QKV projection output [batch*tokens][2304] (q | k | v, head h
 // at columns 64h), keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
 // Replaces F.scaled_dot_product_attention on the reference path (HF:modeling_audio_spectrogram_transformer.py:162-176).
+#include <stdlib.h>
+
 #include "zk_b200.h"
 #include "zk_common.cuh"
 #include "zk_internal.cuh"
@@ -33,6 +35,118 @@ constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
 constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V) is MN-major
 constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
 
+// exp2 on the FMA pipe for a pair of arguments (the MUFU unit does 16 ex2 / clk / SM and is the attention bottleneck at
+// head_dim 64): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax 2^f (max rel. error 7.5e-5, far
+// below the bf16 rounding of P), exponent patched in with one integer multiply-add.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = fadd2(x, magic);
+  const float2 n = fadd2(t, nmagic);
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = ffma2(make_float2(0.055171459913253784f, 0.055171459913253784f), f,
+                   make_float2(0.2426108568906784f, 0.2426108568906784f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// One key block of the online softmax for one query row (see the kernel comment).  RAGGED = the last key block,
+// whose keys >= kmax are masked to -inf; the common instantiation carries no masking instructions at all.
+// POLY = how many of every four element pairs take the FMA-pipe exp2 instead of MUFU.EX2.
+template <bool RAGGED, int POLY>
+__device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_lane, uint32_t sp_row, int row,
+                                              uint64_t* pv_done, float& m, float2& l2a, float2& l2b) {
+  uint32_t buf[2][32];
+  // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  tmem_ld32(t_lane + TM_S, buf[0]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = buf[c & 1];
+    if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
+    if (RAGGED) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;  // -inf
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      mx0 = fmax3(mx0, __uint_as_float(cur[i + 0]), __uint_as_float(cur[i + 1]));
+      mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+      mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
+      mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
+    }
+    if (c < 3) tmem_ld_wait();
+  }
+  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  tmem_ld32(t_lane + TM_S, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
+  bool waited_pv = false;
+  if (j == 0) {
+    m = mx;
+  } else if (__any_sync(0xffffffffu, (mx - m) * SCALE_LOG2E > RESCALE_TAU)) {
+    // rare: advance the running maximum and rescale the accumulator in TMEM (whole warp, tcgen05 is collective)
+    const float mn = fmaxf(m, mx);
+    const float alpha = fast_exp2((m - mn) * SCALE_LOG2E);
+    m = mn;
+    l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
+    mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
+    waited_pv = true;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(t_lane + TM_O + c * 32, buf[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) buf[1][i] = __float_as_uint(__uint_as_float(buf[1][i]) * alpha);
+      tmem_st32(t_lane + TM_O + c * 32, buf[1]);
+    }
+    tmem_st_wait();
+  }
+  // ---- pass 2: p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of the A operand of P V
+  const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
+  const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
+  tmem_ld_wait();
+  if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = buf[c & 1];
+    if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
+    if (RAGGED) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float2 xa = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, mb2);
+      const float2 xb = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, mb2);
+      // pairs are numbered i/2; out of every four, the first POLY go to the FMA pipe
+      const float2 pa = (((i >> 1) & 3) < POLY) ? exp2_poly2(xa) : make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+      const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+      l2a = fadd2(l2a, pa);
+      l2b = fadd2(l2b, pb);
+      pk[i >> 1] = pack_bf16(pa.x, pa.y);
+      pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
+    }
+    // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
+    const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
+      st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    }
+    if (c < 3) tmem_ld_wait();
+  }
+}
+
+template <int POLY>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int tokens) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -130,89 +244,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
-      const bool ragged = kmax < BKV;
-      uint32_t buf[2][32];
-      // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      tmem_ld32(t_lane + TM_S, buf[0]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = buf[c & 1];
-        if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kmax) cur[i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(cur[i + 0]), __uint_as_float(cur[i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
-          mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
-        }
-        if (c < 3) tmem_ld_wait();
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      tmem_ld32(t_lane + TM_S, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
-      bool waited_pv = false;
-      if (j == 0) {
-        m = mx;
-      } else if (__any_sync(0xffffffffu, (mx - m) * SCALE_LOG2E > RESCALE_TAU)) {
-        // rare: advance the running maximum and rescale the accumulator in TMEM (whole warp, tcgen05 is collective)
-        const float mn = fmaxf(m, mx);
-        const float alpha = fast_exp2((m - mn) * SCALE_LOG2E);
-        m = mn;
-        l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
-        mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
-        waited_pv = true;
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(t_lane + TM_O + c * 32, buf[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) buf[1][i] = __float_as_uint(__uint_as_float(buf[1][i]) * alpha);
-          tmem_st32(t_lane + TM_O + c * 32, buf[1]);
-        }
-        tmem_st_wait();
-      }
-      // ---- pass 2: p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of the A operand of P V
-      const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
-      const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
-      tmem_ld_wait();
-      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = buf[c & 1];
-        if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kmax) cur[i] = 0xff800000u;
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float2 xa = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, mb2);
-          const float2 xb = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, mb2);
-          const float2 pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
-          const float2 pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-          l2a = fadd2(l2a, pa);
-          l2b = fadd2(l2b, pb);
-          pk[i >> 1] = pack_bf16(pa.x, pa.y);
-          pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
-        }
-        // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
-        const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
-          st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-        if (c < 3) tmem_ld_wait();
-      }
+      if (kmax < BKV)
+        softmax_block<true, POLY>(j, kmax, t_lane, sp_row, row, pv_done, m, l2a, l2b);
+      else
+        softmax_block<false, POLY>(j, kmax, t_lane, sp_row, row, pv_done, m, l2a, l2b);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_full);
@@ -263,16 +298,25 @@ int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream
     set_error("attention_bf16: batch %d > 65535", batch);
     return ZK_ERR_SHAPE;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
+  static int poly = -1;  // share of exp2 evaluated on the FMA pipe: 0, 1 or 2 of every 4 pairs (ZK_ATTN_POLY overrides)
+  if (poly < 0) {
+    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const char* e = getenv("ZK_ATTN_POLY");
+    poly = e ? atoi(e) : 1;
+    if (poly < 0 || poly > 2) poly = 1;
   }
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
   dim3 grid((tokens + BQ - 1) / BQ, HEADS, batch);
   ProfScope prof(ZK_K_ATTENTION, stream);
-  attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+  if (poly == 0)
+    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+  else if (poly == 1)
+    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+  else
+    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
 }
