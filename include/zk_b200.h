@@ -181,6 +181,9 @@ int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, floa
  * softmax(q k^T / 8) v per (window, head), no mask (HF:modeling...:150-181). */
 int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream);
 int zk_f32_to_bf16(const float* d_in, void* d_out, int64_t n, zk_stream_t stream);
+/* zk_attention_bf16 + a device-clock timeline of the first 512 CTAs (128 int64 slots each; tuning aid, see
+ * scripts/attn_trace.py for the slot layout). */
+int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, int64_t* d_trace, zk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Launch accounting (bench.py): every kernel launch of the library is counted per class; with

@@ -76,6 +76,7 @@ SIGNATURES = {
                                     C.c_void_p]),
     "zk_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "zk_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "zk_attention_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "zk_prof_enable": (None, [C.c_int]),
     "zk_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zk_kernel_class_name": (C.c_char_p, [C.c_int]),

@@ -1,18 +1,15 @@
 // Fused non-causal attention for sm_100a: O = softmax(Q K^T / sqrt(64)) V per (window, head), head_dim 64.
-// One CTA = 128 queries of one (window, head); two CTAs are co-resident per SM (113 KiB smem, 256 TMEM
+// One CTA = 128 queries of one (window, head); two CTAs are co-resident per SM (114 KiB smem, 256 TMEM
 // columns each) so one CTA's softmax overlaps the other's MMAs.
 //
 //   warp 0      TMA producer: Q tile once, then a 2-stage ring of {K_j, V_j} 128x64 bf16 tiles
 //   warp 1      TMEM allocator + MMA issuer:  S = Q K_j^T (UMMA 128x128x16, TMEM cols [0,128)),
-//               O += P_j V_j (UMMA 128x64x16, V as MN-major operand, TMEM cols [128,192))
-//   warps 2..9  softmax, TWO threads per query row (warps w and w+4 share a TMEM lane quarter and take the
-//               two 64-key halves of the row; 16 softmax warps per SM keep the MUFU pipe busy): each thread
-//               pulls its 64 scores out of TMEM once, FMNMX3 max, the two halves agree on the block maximum
-//               through a 2-byte shared-memory exchange, exp2 (FFMA2 + MUFU, optionally part on the FMA pipe),
-//               FADD2 row sums, and P_j goes to 128B-swizzled shared memory as the bf16 A operand of the
-//               second MMA.  O accumulates in TMEM across key blocks; the running maximum is only advanced
-//               (and O rescaled in TMEM, a rare tcgen05.ld/st round trip) when a block maximum exceeds it by
-//               more than 2^8, so the common path never touches O.
+//               O_j = P_j V_j (UMMA 128x64x16, V as MN-major operand, TMEM cols 128 + 64*(j&1))
+//   warps 2..5  softmax: one query row per thread; the whole 128-wide S row is pulled out of TMEM in one burst,
+//               fp32 max (FMNMX3) / exp2 (FFMA2 + MUFU) / sum (FADD2), P_j written to 128B-swizzled shared
+//               memory as the bf16 A operand of the second MMA.  O accumulates in TMEM across key blocks;
+//               the running maximum is only advanced (and O rescaled in TMEM, a rare tcgen05.ld/st round
+//               trip) when a block maximum exceeds it by more than 2^8, so the common path never touches O.
 //
 // Q, K and V are read in place from the fused QKV projection output [batch*tokens][2304] (q | k | v, head h
 // at columns 64h), keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
@@ -30,10 +27,8 @@ constexpr int BQ = 128, BKV = 128, D = 64, HEADS = 12, HID = HEADS * D, KV_STAGE
 constexpr int TILE_BYTES = 128 * 64 * 2;  // one 128 x 64 bf16 tile (Q, K_j or V_j)
 constexpr int P_BYTES = BQ * BKV * 2;
 constexpr int OFF_Q = 0, OFF_KV = TILE_BYTES, OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES, OFF_BAR = OFF_P + P_BYTES;
-constexpr int OFF_XCHG = OFF_BAR + 128;           // [2 halves][128 rows] bf16-rounded block maxima
-constexpr int SMEM_BYTES = OFF_XCHG + 2 * BQ * 2;
-static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
-constexpr int SOFTMAX_WARPS = 8, THREADS = 64 + SOFTMAX_WARPS * 32;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256, TM_S = 0, TM_O = 128;
 constexpr float RESCALE_TAU = 8.0f;  // in log2 units: p <= 2^8 with a stale maximum
 constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
@@ -60,115 +55,100 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
-__device__ __forceinline__ void pair_barrier(int quarter) {  // the two warps that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-}
-
-// bf16 value >= x (round toward +inf): both halves of a row must derive the SAME reference maximum from the exchange.
-__device__ __forceinline__ uint32_t bf16_ceil_bits(float x) {
-  const uint32_t b = __float_as_uint(x);
-  return ((x >= 0.f) ? (b + 0xffffu) : b) >> 16;
-}
-
-struct RowState {
-  float m;           // reference maximum of the row (raw score units), identical in both half-row threads
-  float2 l2a, l2b;   // partial sums of this thread's half row
-};
-
-// One key block for one half row.  RAGGED = the last key block (keys >= kmax masked to -inf); the common
-// instantiation carries no masking instructions.  POLY of every four element pairs use the FMA-pipe exp2.
+// One key block of the online softmax for one query row (see the kernel comment).  RAGGED = the last key block,
+// whose keys >= kmax are masked to -inf; the common instantiation carries no masking instructions at all.
+// POLY = how many of every four element pairs take the FMA-pipe exp2 instead of MUFU.EX2.
 template <bool RAGGED, int POLY>
-__device__ __forceinline__ void softmax_block(int j, int kmax, int half, int quarter, int row, uint32_t t_lane,
-                                              uint32_t sp_row, uint16_t* xchg, uint64_t* pv_done, RowState& st) {
-  float mine;
-  {  // ---- pass 1: maximum of this thread's 64 scores (both 32-column chunks in flight together)
-    uint32_t s0[32], s1[32];
-    tmem_ld32(t_lane + TM_S + half * 64, s0);
-    tmem_ld32(t_lane + TM_S + half * 64 + 32, s1);
-    tmem_ld_wait();
-    if (RAGGED) {
+__device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_lane, uint32_t sp_row, int row,
+                                              uint64_t* pv_done, float& m, float2& l2a, float2& l2b) {
+  uint32_t buf[2][32];
+  // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  tmem_ld32(t_lane + TM_S, buf[0]);
+  tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (half * 64 + i >= kmax) s0[i] = 0xff800000u;  // -inf
-        if (half * 64 + 32 + i >= kmax) s1[i] = 0xff800000u;
-      }
-    }
-    float mx0 = __uint_as_float(s0[0]), mx1 = __uint_as_float(s0[1]), mx2 = __uint_as_float(s1[0]), mx3 = __uint_as_float(s1[1]);
-#pragma unroll
-    for (int i = 2; i < 32; i += 4) {
-      mx0 = fmax3(mx0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
-      mx2 = fmax3(mx2, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
-      if (i + 3 < 32) {
-        mx1 = fmax3(mx1, __uint_as_float(s0[i + 2]), __uint_as_float(s0[i + 3]));
-        mx3 = fmax3(mx3, __uint_as_float(s1[i + 2]), __uint_as_float(s1[i + 3]));
-      }
-    }
-    mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));  // may be -inf (fully masked half): bf16 -inf is exact
-  }
-  // agree on the block maximum with the thread that owns the other 64 keys of this row
-  const uint32_t mine_b = bf16_ceil_bits(mine);
-  xchg[half * BQ + row] = (uint16_t)mine_b;
-  pair_barrier(quarter);
-  const uint32_t other_b = xchg[(half ^ 1) * BQ + row];
-  const float mx = fmaxf(__uint_as_float(mine_b << 16), __uint_as_float(other_b << 16));
-  bool waited_pv = false;
-  if (j == 0) {
-    st.m = mx;
-  } else if (__any_sync(0xffffffffu, (mx - st.m) * SCALE_LOG2E > RESCALE_TAU)) {
-    // rare: advance the running maximum and rescale the accumulator in TMEM.  Both warps of the pair see the same
-    // 32 (m, mx) pairs, so they take this branch together; each rescales its 32 of the 64 output columns.
-    const float mn = fmaxf(st.m, mx);
-    const float alpha = fast_exp2((st.m - mn) * SCALE_LOG2E);
-    st.m = mn;
-    st.l2a.x *= alpha; st.l2a.y *= alpha; st.l2b.x *= alpha; st.l2b.y *= alpha;
-    mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
-    waited_pv = true;
-    tc_fence_after();
-    uint32_t r[32];
-    tmem_ld32(t_lane + TM_O + half * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-    tmem_st32(t_lane + TM_O + half * 32, r);
-    tmem_st_wait();
-  }
-  // ---- pass 2 (scores re-read from TMEM, 32 columns at a time, to stay inside 96 registers):
-  //      p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of this thread's half of the P V operand
-  const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
-  const float2 mb2 = make_float2(-st.m * SCALE_LOG2E, -st.m * SCALE_LOG2E);
-  const uint32_t atom = sp_row + half * (BQ * 128);  // this thread's 64 keys = swizzle atom `half`, row `row`
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t s[32];
-    tmem_ld32(t_lane + TM_S + half * 64 + c * 32, s);
-    tmem_ld_wait();
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = buf[c & 1];
+    if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
     if (RAGGED) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (half * 64 + c * 32 + i >= kmax) s[i] = 0xff800000u;
+        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;  // -inf
     }
 #pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      mx0 = fmax3(mx0, __uint_as_float(cur[i + 0]), __uint_as_float(cur[i + 1]));
+      mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+      mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
+      mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
+    }
+    if (c < 3) tmem_ld_wait();
+  }
+  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  tmem_ld32(t_lane + TM_S, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
+  bool waited_pv = false;
+  if (j == 0) {
+    m = mx;
+  } else if (__any_sync(0xffffffffu, (mx - m) * SCALE_LOG2E > RESCALE_TAU)) {
+    // rare: advance the running maximum and rescale the accumulator in TMEM (whole warp, tcgen05 is collective)
+    const float mn = fmaxf(m, mx);
+    const float alpha = fast_exp2((m - mn) * SCALE_LOG2E);
+    m = mn;
+    l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
+    mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
+    waited_pv = true;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(t_lane + TM_O + c * 32, buf[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) buf[1][i] = __float_as_uint(__uint_as_float(buf[1][i]) * alpha);
+      tmem_st32(t_lane + TM_O + c * 32, buf[1]);
+    }
+    tmem_st_wait();
+  }
+  // ---- pass 2: p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of the A operand of P V
+  const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
+  const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
+  tmem_ld_wait();
+  if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = buf[c & 1];
+    if (c < 3) tmem_ld32(t_lane + TM_S + (c + 1) * 32, buf[(c + 1) & 1]);
+    if (RAGGED) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;
+    }
+    uint32_t pk[16];
+#pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float2 xa = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, mb2);
-      const float2 xb = ffma2(make_float2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), sc2, mb2);
+      const float2 xa = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, mb2);
+      const float2 xb = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, mb2);
       // pairs are numbered i/2; out of every four, the first POLY go to the FMA pipe
       const float2 pa = (((i >> 1) & 3) < POLY) ? exp2_poly2(xa) : make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
       const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-      st.l2a = fadd2(st.l2a, pa);
-      st.l2b = fadd2(st.l2b, pb);
-      s[i >> 1] = pack_bf16(pa.x, pa.y);  // in place: s[0..15] end up holding the 32 probabilities
-      s[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
+      l2a = fadd2(l2a, pa);
+      l2b = fadd2(l2b, pb);
+      pk[i >> 1] = pack_bf16(pa.x, pa.y);
+      pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
     }
-    if (c == 0 && j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free once P_{j-1} V_{j-1} is done
+    // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
+    const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(atom + ((uint32_t)((c * 4 + q) ^ (row & 7)) << 4), s[q * 4 + 0], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
+      st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    }
+    if (c < 3) tmem_ld_wait();
   }
 }
 
 template <int POLY>
 __global__ void __launch_bounds__(THREADS, 2)
-attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int tokens) {
+attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int tokens, long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;
@@ -178,12 +158,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
   uint64_t* p_full = bars + 6;
   uint64_t* pv_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  uint16_t* xchg = reinterpret_cast<uint16_t*>(smem + OFF_XCHG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (tokens + BKV - 1) / BKV;
   const int row_base = b * tokens;  // first row of this window in the [batch*tokens] matrices
+  // optional timeline capture (zk_attention_trace): 128 slots per CTA for the first 512 CTAs of the grid
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* tr = (trace && cta_lin < 512) ? trace + (long long)cta_lin * 128 : nullptr;
+  if (tr && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[0] = smid;
+    tr[1] = clock64();
+  }
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -198,7 +186,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
     }
     mbar_init(pv_done, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, SOFTMAX_WARPS * 32);
+    mbar_init(p_full, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -238,7 +226,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(p_full, j & 1);  // P_j is in smem and S_j has been read out of TMEM
         tc_fence_after();
+        if (tr) tr[8 + j * 8 + 4] = clock64();
         if (j + 1 < nkv) issue_s(j + 1);
+        if (tr) tr[8 + j * 8 + 5] = clock64();
         const int st = j & 1;
         const uint32_t sv = smem_u32(smem + OFF_KV + st * 2 * TILE_BYTES + TILE_BYTES);
         const uint32_t d_o = tmem_base + TM_O;
@@ -251,54 +241,55 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
+        if (tr) tr[8 + j * 8 + 6] = clock64();
       }
     }
   } else {
-    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which 64 keys of every block (and which 32 output columns)
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sp_row = smem_u32(smem + OFF_P) + row * 128;
-    RowState st;
-    st.m = -INFINITY;
-    st.l2a = make_float2(0.f, 0.f);
-    st.l2b = make_float2(0.f, 0.f);
+    float m = -INFINITY;
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
 
     for (int j = 0; j < nkv; ++j) {
+      if (tr && warp == 2 && lane == 0) tr[8 + j * 8 + 0] = clock64();
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      if (tr && warp == 2 && lane == 0) tr[8 + j * 8 + 1] = clock64();
       const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
       if (kmax < BKV)
-        softmax_block<true, POLY>(j, kmax, half, quarter, row, t_lane, sp_row, xchg, pv_done, st);
+        softmax_block<true, POLY>(j, kmax, t_lane, sp_row, row, pv_done, m, l2a, l2b);
       else
-        softmax_block<false, POLY>(j, kmax, half, quarter, row, t_lane, sp_row, xchg, pv_done, st);
+        softmax_block<false, POLY>(j, kmax, t_lane, sp_row, row, pv_done, m, l2a, l2b);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_full);
+      if (tr && warp == 2 && lane == 0) tr[8 + j * 8 + 2] = clock64();
     }
+    if (tr && warp == 2 && lane == 0) tr[2] = clock64();
     {
       const int jl = nkv - 1;
-      mbar_wait(pv_done, jl & 1);  // O is final; the P buffer is free and carries the two half-row sums across
+      mbar_wait(pv_done, jl & 1);
       tc_fence_after();
-      float* lsum = reinterpret_cast<float*>(smem + OFF_P);
-      const float mine = (st.l2a.x + st.l2a.y) + (st.l2b.x + st.l2b.y);
-      lsum[half * BQ + row] = mine;
-      pair_barrier(quarter);
-      const float inv = 1.0f / (mine + lsum[(half ^ 1) * BQ + row]);
+      const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
       const int q = qb * BQ + row;
-      __nv_bfloat16* dst = out + (long long)(row_base + q) * HID + h * D + half * 32;
-      uint32_t r[32];
-      tmem_ld32(t_lane + TM_O + half * 32, r);
-      tmem_ld_wait();
-      if (q < tokens) {
+      __nv_bfloat16* dst = out + (long long)(row_base + q) * HID + h * D;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
-          v.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
-          v.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
-          v.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + g * 8) = v;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TM_O + c * 32, r);
+        tmem_ld_wait();
+        if (q < tokens) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = v;
+          }
         }
       }
     }
@@ -311,7 +302,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
 
 }  // namespace attn
 
-int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream_t stream) {
+int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long long* trace, cudaStream_t stream) {
   using namespace attn;
   int rc = device_check();
   if (rc) return rc;
@@ -337,16 +328,24 @@ int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream
   dim3 grid((tokens + BQ - 1) / BQ, HEADS, batch);
   ProfScope prof(ZK_K_ATTENTION, stream);
   if (poly == 0)
-    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, trace);
   else if (poly == 1)
-    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, trace);
   else
-    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens);
+    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, trace);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
 }
 
+int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream_t stream) {
+  return attention_bf16_impl(qkv, out, batch, tokens, nullptr, stream);
+}
+
 }  // namespace zk
+
+extern "C" int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, int64_t* d_trace, zk_stream_t stream) {
+  return zk::attention_bf16_impl(d_qkv, d_out, batch, tokens, reinterpret_cast<long long*>(d_trace), (cudaStream_t)stream);
+}
 
 extern "C" int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream) {
   return zk::attention_bf16(d_qkv, d_out, batch, tokens, (cudaStream_t)stream);
