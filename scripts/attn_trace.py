@@ -38,6 +38,13 @@ for c in range(512):
     for j in range(1, 9):
         r = t[c, 8 + 8 * j: 16 + 8 * j]
         d.append((r[1] - r[0], r[2] - r[1], r[4] - r[2], t[c, 8 + 8 * (j + 1) + 1] - r[2]))
+e = []
+for c in range(512):
+    for j in range(1, 9):
+        r = t[c, 8 + 8 * j: 16 + 8 * j]
+        e.append((r[3] - r[1], r[7] - r[3], r[2] - r[7]))
+e = np.array(e)
+print("softmax split (median): pass 1 (max) %d | rescale check + wait for P V_{j-1} %d | pass 2 (exp, pack, store) %d" % tuple(np.median(e, axis=0)))
 d = np.array(d)
 print("median cycles: wait for S %d | softmax (S ready -> P published) %d | P published -> MMA thread sees it %d | P published -> next S ready %d"
       % tuple(np.median(d, axis=0)))

@@ -65,7 +65,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // POLY = how many of every four element pairs take the FMA-pipe exp2 instead of MUFU.EX2.
 template <bool RAGGED, int POLY>
 __device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_s, uint32_t t_o, uint32_t sp_row, int row,
-                                              uint64_t* pv_done, float& m, float2& l2a, float2& l2b) {
+                                              uint64_t* pv_done, float& m, float2& l2a, float2& l2b, long long* trj) {
   uint32_t buf[2][32];
   // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -90,6 +90,7 @@ __device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_s, uin
     if (c < 3) tmem_ld_wait();
   }
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  if (trj) trj[3] = clock64();
   tmem_ld32(t_s, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
   bool waited_pv = false;
   if (j == 0) {
@@ -118,6 +119,7 @@ __device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_s, uin
   const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
   tmem_ld_wait();
   if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
+  if (trj) trj[7] = clock64();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t(&cur)[32] = buf[c & 1];
@@ -287,9 +289,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
       if (tracer) tr[8 + j * 8 + 1] = clock64();
       const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
       if (kmax < BKV)
-        softmax_block<true, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b);
+        softmax_block<true, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b, tracer ? tr + 8 + j * 8 : nullptr);
       else
-        softmax_block<false, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b);
+        softmax_block<false, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b, tracer ? tr + 8 + j * 8 : nullptr);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(&p_full[t]);
@@ -351,8 +353,8 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
     ZK_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ZK_CUDA(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const char* e = getenv("ZK_ATTN_POLY");
-    poly = e ? atoi(e) : 0;
-    if (poly < 0 || poly > 2) poly = 0;
+    poly = e ? atoi(e) : 1;
+    if (poly < 0 || poly > 2) poly = 1;
   }
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
