@@ -21,31 +21,21 @@ for _ in range(2):
     _lib.check(lib.zk_attention_trace(qkv.data_ptr(), out.data_ptr(), B, T, trace.data_ptr(), _lib.stream_ptr()), "trace")
 torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(512, 128)
-by_sm = {}
-for c in range(512):
-    by_sm.setdefault(int(t[c, 0]), []).append(c)
-print("CTAs per SM among the first 512:", sorted(len(v) for v in by_sm.values())[-5:])
-for sm in sorted(by_sm)[:2]:
-    ctas = sorted(by_sm[sm], key=lambda c: t[c, 1])[:4]
-    t0 = min(t[c, 1] for c in ctas)
-    for c in ctas:
-        print(f"SM {sm} CTA {c}: start {t[c,1]-t0}, softmax end {t[c,2]-t0} (total {t[c,2]-t[c,1]})")
-        for j in range(10):
-            r = t[c, 8 + 8 * j: 16 + 8 * j] - t0
-            print(f"   j={j}: wait_S {r[0]:7d} S_ready {r[1]:7d} (+{r[1]-r[0]:5d}) P_pub {r[2]:7d} (softmax {r[2]-r[1]:5d}) | mma sees P {r[4]:7d} (+{r[4]-r[2]:4d}) S_next issued {r[5]:7d} PV issued {r[6]:7d}")
+ncta = min(512, torch.cuda.get_device_properties(0).multi_processor_count)
+# slots per block n (first 15 blocks of each CTA, tile A): +0 softmax starts waiting for S_n, +1 S_n ready,
+# +3 S_n in registers (buffer handed back), +7 max / rescale done, +2 P_n published; MMA thread: +5 S_n issued, +6 P_n V_n issued
+for c in range(2):
+    t0 = t[c, 1]
+    print(f"CTA {c} on SM {t[c,0]}: first item done at +{t[c,2]-t0}")
+    for n in range(15):
+        r = t[c, 8 + 8 * n: 16 + 8 * n] - t0
+        print(f"   n={n:2d}: S issued {r[5]:7d} | wait {r[0]:7d} S_ready {r[1]:7d} (+{r[1]-r[0]:5d}) loaded {r[3]-r[1]:5d} max {r[7]-r[3]:5d} exp+store {r[2]-r[7]:5d} -> P_pub {r[2]:7d} | PV issued {r[6]:7d} (+{r[6]-r[2]:4d})")
 d = []
-for c in range(512):
-    for j in range(1, 9):
-        r = t[c, 8 + 8 * j: 16 + 8 * j]
-        d.append((r[1] - r[0], r[2] - r[1], r[4] - r[2], t[c, 8 + 8 * (j + 1) + 1] - r[2]))
-e = []
-for c in range(512):
-    for j in range(1, 9):
-        r = t[c, 8 + 8 * j: 16 + 8 * j]
-        e.append((r[3] - r[1], r[7] - r[3], r[2] - r[7]))
-e = np.array(e)
-print("softmax split (median): pass 1 (max) %d | rescale check + wait for P V_{j-1} %d | pass 2 (exp, pack, store) %d" % tuple(np.median(e, axis=0)))
+for c in range(ncta):
+    for n in range(2, 14):
+        r = t[c, 8 + 8 * n: 16 + 8 * n]
+        nx = t[c, 8 + 8 * (n + 1): 16 + 8 * (n + 1)]
+        d.append((r[1] - r[0], r[3] - r[1], r[7] - r[3], r[2] - r[7], nx[2] - r[2]))
 d = np.array(d)
-print("median cycles: wait for S %d | softmax (S ready -> P published) %d | P published -> MMA thread sees it %d | P published -> next S ready %d"
-      % tuple(np.median(d, axis=0)))
-print("mean   cycles: %d %d %d %d ; per-block period %d" % (*d.mean(axis=0), (d[:, 1] + d[:, 3]).mean()))
+print("median cycles: wait for S %d | load S %d | max %d | exp + P store %d | block period %d" % tuple(np.median(d, axis=0)))
+print("mean   cycles: %d %d %d %d %d" % tuple(d.mean(axis=0)))

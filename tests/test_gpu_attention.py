@@ -13,7 +13,8 @@ def _ref(qkv, B, T):
 
 
 @pytest.mark.parametrize("B,T,scale", [(2, 1214, 1.0), (1, 128, 1.0), (1, 129, 1.0), (3, 300, 3.0), (1, 62, 1.0),
-                                       (1, 1214, 6.0)])
+                                       (1, 1214, 6.0),
+                                       (16, 1214, 2.0), (40, 200, 4.0)])  # > 148 work items: persistent CTAs walk several
 def test_attention(B, T, scale):
     from zenker_audio_detection_b200 import ops
 
@@ -25,6 +26,8 @@ def test_attention(B, T, scale):
     torch.cuda.synchronize()
     ref = _ref(qkv, B, T)
     err = (out.float() - ref).abs().max().item()
-    assert err <= 2e-2, err  # P is rounded to bf16 (2^-9) before the PV product; |v| ~ 1..4
+    # bf16 output: half an ulp at |o| in [4, 8) is 1.56e-2 on its own, plus the bf16 rounding of P (2^-9 relative)
+    # against an fp32 row sum: 2^-9 * |v|max ~ 8e-3 for a one-hot row (scale 6 makes most rows one-hot)
+    assert err <= 3e-2, err
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel <= 1e-2, rel

@@ -1,21 +1,24 @@
 // Fused non-causal attention for sm_100a: O = softmax(Q K^T / sqrt(64)) V per (window, head), head_dim 64.
-// One persistent-size CTA per SM handles 256 queries of one (window, head) as TWO 128-row tiles (A, B) that share the
-// K/V stream and run their softmax in anti-phase: while tile A's softmax warps own the MUFU pipe, the tensor core
-// produces tile B's next scores, and vice versa (at head_dim 64 the 16-lane MUFU pipe, not the tensor pipe, bounds
-// attention: 128x128 exp2 per block = 1024 cycles vs 512 cycles of MMA).
 //
-//   warp 0       TMA producer: both Q tiles once, then a 3-stage ring of {K_j, V_j} 128x64 bf16 tiles
-//   warp 1       TMEM allocator + MMA issuer, per tile t in {A, B}:
-//                  S_t = Q_t K_j^T   (UMMA 128x128x16, TMEM cols [128 t, 128 t + 128))
-//                  O_t += P_t V_j    (UMMA 128x64x16, V as MN-major operand, TMEM cols [256 + 64 t, +64))
-//   warps 4..7   softmax of tile A, warps 8..11 of tile B: one query row per thread, S pulled out of TMEM in
-//                double-buffered 32-column chunks, fp32 max (FMNMX3) / exp2 (FFMA2 + MUFU, optionally part on the
-//                FMA pipe) / sum (FADD2), P written to 128B-swizzled shared memory as the bf16 A operand of the
-//                second MMA.  O accumulates in TMEM across key blocks; the running maximum is only advanced (and O
-//                rescaled in TMEM, a rare tcgen05.ld/st round trip) when a block maximum exceeds it by more than 2^8.
+// Persistent kernel, one CTA per SM.  A work item is 256 queries of one (window, head), processed as TWO 128-row tiles
+// (A, B) that share the K/V stream; the CTA walks its items back to back so the K/V ring, the tensor pipe and the
+// softmax warps never drain between items.
+//
+//   warp 0       TMA producer: {Q_A, Q_B} of the next item (double buffered), 4-stage ring of {K_j, V_j} 128x64 tiles
+//   warps 1, 2   MMA issuers of tile A / tile B (warp 1 also owns the TMEM allocation), per tile t:
+//                  S_t  = Q_t K_j^T   (UMMA 128x128x16 SS, TMEM cols [128 t, +128))
+//                  O_t += P_t V_j     (UMMA 128x64x16  TS: P is read from TMEM, V_j is the MN-major smem operand)
+//   warps 4..7   softmax of tile A, warps 8..11 of tile B (216 registers each via setmaxnreg): one query row per
+//                thread.  The whole 128-key score row is pulled out of TMEM ONCE into registers and the S buffer is
+//                handed back to the tensor core at that point, so S_t(j+1) is computed underneath the exponentials of
+//                block j.  fp32 max (FMNMX3) / exp2 (FFMA2 + MUFU, 1/4 on the FMA pipe) / sum (FADD2); P goes back
+//                to TMEM as packed bf16 pairs (tcgen05.st), not through shared memory: at head_dim 64 the 128 B/clk
+//                shared-memory port is as scarce as the 16-lane MUFU pipe, and the smem round trip of P was 57 % of
+//                the operand traffic.  O accumulates in TMEM across key blocks; the running maximum is only advanced
+//                (and O rescaled in TMEM, a rare tcgen05.ld/st round trip) when a block maximum exceeds it by 2^8.
 //
 // Q, K and V are read in place from the fused QKV projection output [batch*tokens][2304] (q | k | v, head h
-// at columns 64h), keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
+// at columns 64h); keys beyond `tokens` are masked to -inf (1214 = 9*128 + 62).
 // Replaces F.scaled_dot_product_attention on the reference path (HF:modeling_audio_spectrogram_transformer.py:162-176).
 #include <stdlib.h>
 
@@ -26,19 +29,24 @@
 namespace zk {
 namespace attn {
 
-constexpr int BQ = 128, BKV = 128, D = 64, HEADS = 12, HID = HEADS * D, KV_STAGES = 3, QTILES = 2;
+constexpr int BQ = 128, BKV = 128, D = 64, HEADS = 12, HID = HEADS * D, KV_STAGES = 4, QTILES = 2;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // one 128 x 64 bf16 tile (Q_t, K_j or V_j)
-constexpr int P_BYTES = BQ * BKV * 2;
-constexpr int OFF_Q = 0, OFF_KV = QTILES * TILE_BYTES, OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES,
-              OFF_BAR = OFF_P + QTILES * P_BYTES;
+constexpr int OFF_Q = 0;                                   // [2 item parities][2 tiles]
+constexpr int OFF_KV = 2 * QTILES * TILE_BYTES;            // [KV_STAGES]{K, V}
+constexpr int OFF_STG = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [2 tiles] 128 x 64 bf16 output staging (TMA store)
+constexpr int OFF_BAR = OFF_STG + QTILES * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr int THREADS = 384;  // warps 0-3: producer, MMA, 2 spare; 4-7: softmax A; 8-11: softmax B
-constexpr uint32_t TMEM_COLS = 512, TM_S = 0, TM_O = 256;  // S_t at 128 t, O_t at 256 + 64 t
-constexpr float RESCALE_TAU = 8.0f;  // in log2 units: p <= 2^8 with a stale maximum
+constexpr int THREADS = 384;  // warps 0-3: producer, MMA A, MMA B, spare; 4-7: softmax A; 8-11: softmax B
+// TMEM columns: S_t at 128 t (fp32), O_t at 256 + 64 t (fp32), P_t at 384 + 64 t (bf16 pairs, 128 keys)
+constexpr uint32_t TMEM_COLS = 512, TM_S = 0, TM_O = 256, TM_P = 384;
+constexpr float RESCALE_TAU = 24.0f;  // log2 units: p <= 2^24 against a stale maximum (fp32 sums / bf16 P keep their
+                                     // relative precision; 1214 keys * 2^24 * |v| is nowhere near fp32 range)
 constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
 constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V) is MN-major
 constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
+constexpr int REGS_SOFTMAX = 216, REGS_OTHER = 56;
+static_assert(128 * REGS_OTHER + 256 * REGS_SOFTMAX <= 65536, "register file");
 
 // exp2 on the FMA pipe for a pair of arguments (the MUFU unit does 16 ex2 / clk / SM and is the attention bottleneck at
 // head_dim 64): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax 2^f (max rel. error 7.5e-5, far
@@ -60,120 +68,171 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
-// One key block of the online softmax for one query row (see the kernel comment).  RAGGED = the last key block,
-// whose keys >= kmax are masked to -inf; the common instantiation carries no masking instructions at all.
-// POLY = how many of every four element pairs take the FMA-pipe exp2 instead of MUFU.EX2.
-template <bool RAGGED, int POLY>
-__device__ __forceinline__ void softmax_block(int j, int kmax, uint32_t t_s, uint32_t t_o, uint32_t sp_row, int row,
-                                              uint64_t* pv_done, float& m, float2& l2a, float2& l2b, long long* trj) {
-  uint32_t buf[2][32];
-  // ---- pass 1: row maximum (TMEM reads are double buffered against the FMNMX3 chains)
-  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-  tmem_ld32(t_s, buf[0]);
+// A D-operand MMA with A in tensor memory (P as packed bf16 pairs: lane = query row, 8 columns per 16 keys).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// 32 consecutive columns into r[OFF .. OFF+32) of a larger register array
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld32_at(uint32_t taddr, uint32_t (&r)[N]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+        "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+        "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15]), "=r"(r[OFF + 16]),
+        "=r"(r[OFF + 17]), "=r"(r[OFF + 18]), "=r"(r[OFF + 19]), "=r"(r[OFF + 20]), "=r"(r[OFF + 21]),
+        "=r"(r[OFF + 22]), "=r"(r[OFF + 23]), "=r"(r[OFF + 24]), "=r"(r[OFF + 25]), "=r"(r[OFF + 26]),
+        "=r"(r[OFF + 27]), "=r"(r[OFF + 28]), "=r"(r[OFF + 29]), "=r"(r[OFF + 30]), "=r"(r[OFF + 31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct SoftmaxState {
+  float m;
+  float2 l2a, l2b;
+};
+
+// One key block of the online softmax for one query row.  FIRST = first key block of the work item, `n` = running
+// block number of this tile across items (mbarrier parities), RAGGED = the last key block, whose keys >= kmax are
+// masked to -inf.  POLY = how many of every four element pairs take the FMA-pipe exp2 instead of MUFU.EX2.
+//
+// Only the first block of an item needs its row maximum before the exponentials.  Every later block exponentiates
+// against the running (possibly stale) maximum straight away and computes its own maximum alongside (FMNMX3 on the
+// ALU pipe, independent of the MUFU stream); only if some row of the warp then turns out to exceed the running maximum
+// by more than 2^8 is the accumulator rescaled and the block redone from the scores still held in registers.  That
+// keeps a warp's MUFU demand uniform over the block instead of 0 % during a max phase and 100 % after it, which is
+// what lets the two softmax warps of a scheduler share the MUFU pipe without phase locking.
+template <bool RAGGED, bool FIRST, int POLY>
+__device__ __forceinline__ void softmax_block(uint32_t n, int kmax, uint32_t t_s, uint32_t t_o, uint32_t t_p,
+                                              uint64_t* s_free, uint64_t* pv_done, SoftmaxState& st, long long* trj) {
+  uint32_t s[128];
+  tmem_ld32_at<0>(t_s, s);
+  tmem_ld32_at<32>(t_s + 32, s);
+  tmem_ld32_at<64>(t_s + 64, s);
+  tmem_ld32_at<96>(t_s + 96, s);
   tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t(&cur)[32] = buf[c & 1];
-    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, buf[(c + 1) & 1]);
-    if (RAGGED) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;  // -inf
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      mx0 = fmax3(mx0, __uint_as_float(cur[i + 0]), __uint_as_float(cur[i + 1]));
-      mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
-      mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
-      mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
-    }
-    if (c < 3) tmem_ld_wait();
-  }
-  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  tc_fence_before();
+  mbar_arrive(s_free);  // the score buffer may be overwritten by S(j+1) from here on
   if (trj) trj[3] = clock64();
-  tmem_ld32(t_s, buf[0]);  // first chunk of pass 2, in flight across the (rare) rescale
-  bool waited_pv = false;
-  if (j == 0) {
-    m = mx;
-  } else if (__any_sync(0xffffffffu, (mx - m) * SCALE_LOG2E > RESCALE_TAU)) {
-    // rare: advance the running maximum and rescale the accumulator in TMEM (whole warp, tcgen05 is collective)
-    const float mn = fmaxf(m, mx);
-    const float alpha = fast_exp2((m - mn) * SCALE_LOG2E);
-    m = mn;
-    l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
-    mbar_wait(pv_done, (j - 1) & 1);  // O holds every block < j
-    waited_pv = true;
-    tc_fence_after();
+  if (RAGGED) {
+#pragma unroll
+    for (int i = 0; i < 128; ++i)
+      if (i >= kmax) s[i] = 0xff800000u;  // -inf
+  }
+  if (FIRST) {
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; i += 8) {
+      mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+      mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+      mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    st.m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    st.l2a = make_float2(0.f, 0.f);
+    st.l2b = make_float2(0.f, 0.f);
+  }
+  if (trj) trj[7] = clock64();
+  const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
+  float2 lba, lbb;  // row sum of this block
+#pragma unroll 1
+  for (int pass = 0;; ++pass) {
+    // p = exp2(s * c - m * c), row sum, bf16 pack; P goes to TMEM as the A operand of P V (column i = keys 2i, 2i+1)
+    const float2 mb2 = make_float2(-st.m * SCALE_LOG2E, -st.m * SCALE_LOG2E);
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+    lba = make_float2(0.f, 0.f);
+    lbb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const int e = c * 32 + i;
+        const float2 xa = ffma2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), sc2, mb2);
+        const float2 xb = ffma2(make_float2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), sc2, mb2);
+        // pairs are numbered i/2; out of every four, the first POLY go to the FMA pipe
+        const float2 pa = (((i >> 1) & 3) < POLY) ? exp2_poly2(xa) : make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+        const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+        lba = fadd2(lba, pa);
+        lbb = fadd2(lbb, pb);
+        pk[i >> 1] = pack_bf16(pa.x, pa.y);
+        pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
+        if (!FIRST) {
+          if (i & 4) {
+            mx2 = fmax3(mx2, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+            mx3 = fmax3(mx3, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
+          } else {
+            mx0 = fmax3(mx0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
+          }
+        }
+      }
+      if (c == 0 && pass == 0 && n > 0) {
+        mbar_wait(pv_done, (n - 1) & 1);  // the P buffer is free (and O final up to block j-1) once P(j-1) V(j-1) is done
+        tc_fence_after();
+      }
+      tmem_st16(t_p + c * 16, pk);
+    }
+    if (FIRST || pass == 1) break;
+    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    if (!__any_sync(0xffffffffu, (mx - st.m) * SCALE_LOG2E > RESCALE_TAU)) break;
+    // rare: advance the running maximum, rescale the accumulator in TMEM (whole warp, tcgen05 is collective), redo
+    const float mn = fmaxf(st.m, mx);
+    const float alpha = fast_exp2((st.m - mn) * SCALE_LOG2E);
+    st.m = mn;
+    st.l2a.x *= alpha; st.l2a.y *= alpha; st.l2b.x *= alpha; st.l2b.y *= alpha;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      tmem_ld32(t_o + c * 32, buf[1]);
+      uint32_t o[32];
+      tmem_ld32(t_o + c * 32, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) buf[1][i] = __float_as_uint(__uint_as_float(buf[1][i]) * alpha);
-      tmem_st32(t_o + c * 32, buf[1]);
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st32(t_o + c * 32, o);
     }
-    tmem_st_wait();
   }
-  // ---- pass 2: p = exp2(s * c - m * c), row sum, bf16 pack, swizzled store of the A operand of P V
-  const float2 sc2 = make_float2(SCALE_LOG2E, SCALE_LOG2E);
-  const float2 mb2 = make_float2(-m * SCALE_LOG2E, -m * SCALE_LOG2E);
-  tmem_ld_wait();
-  if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer is free once P_{j-1} V_{j-1} has completed
-  if (trj) trj[7] = clock64();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t(&cur)[32] = buf[c & 1];
-    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, buf[(c + 1) & 1]);
-    if (RAGGED) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i >= kmax) cur[i] = 0xff800000u;
-    }
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float2 xa = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, mb2);
-      const float2 xb = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, mb2);
-      // pairs are numbered i/2; out of every four, the first POLY go to the FMA pipe
-      const float2 pa = (((i >> 1) & 3) < POLY) ? exp2_poly2(xa) : make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
-      const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-      l2a = fadd2(l2a, pa);
-      l2b = fadd2(l2b, pb);
-      pk[i >> 1] = pack_bf16(pa.x, pa.y);
-      pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
-    }
-    // keys [32c, 32c+32) = 64 B = four 16-B chunks of swizzle atom (c>>1)
-    const uint32_t atom = sp_row + (c >> 1) * (BQ * 128);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q) ^ (row & 7));
-      st_shared_v4(atom + chunk * 16, pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-    }
-    if (c < 3) tmem_ld_wait();
-  }
+  st.l2a = fadd2(st.l2a, lba);
+  st.l2b = fadd2(st.l2b, lbb);
+  tmem_st_wait();
 }
 
 template <int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
-attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int tokens, int stagger,
-            long long* trace) {
+attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int tokens,
+            int num_items, int qpairs, int stagger, long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2] per tile
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* pv_done = bars + 11;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* q_full = bars;          // [2] item parity
+  uint64_t* q_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars + 4;     // [KV_STAGES]
+  uint64_t* kv_empty = bars + 8;    // [KV_STAGES]
+  uint64_t* s_full = bars + 12;     // [2] per tile
+  uint64_t* s_free = bars + 14;     // [2]
+  uint64_t* p_full = bars + 16;     // [2]
+  uint64_t* pv_done = bars + 18;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (tokens + BKV - 1) / BKV;
-  const int row_base = b * tokens;  // first row of this window in the [batch*tokens] matrices
-  // optional timeline capture (zk_attention_trace): 128 slots per CTA for the first 512 CTAs of the grid
-  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  long long* tr = (trace && cta_lin < 512) ? trace + (long long)cta_lin * 128 : nullptr;
+  const int my_items = ((int)blockIdx.x < num_items) ? (num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // optional timeline capture (zk_attention_trace): 128 slots per CTA, first item of each CTA
+  long long* tr = (trace && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
   if (tr && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -187,13 +246,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
       __trap();
     }
     tma_prefetch_desc(&tm);
-    mbar_init(q_full, 1);
+    tma_prefetch_desc(&tm_out);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);
+    }
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);
     }
     for (int t = 0; t < QTILES; ++t) {
       mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
       mbar_init(&p_full[t], 128);
       mbar_init(&pv_done[t], 1);
     }
@@ -205,124 +269,164 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, QTILES * TILE_BYTES);
-      for (int t = 0; t < QTILES; ++t)
-        tma_load_2d(smem + OFF_Q + t * TILE_BYTES, &tm, q_full, h * D, row_base + (qb * QTILES + t) * BQ);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        uint8_t* dst = smem + OFF_KV + st * 2 * TILE_BYTES;
-        tma_load_2d(dst, &tm, &kv_full[st], HID + h * D, row_base + j * BKV);
-        tma_load_2d(dst + TILE_BYTES, &tm, &kv_full[st], 2 * HID + h * D, row_base + j * BKV);
-        if (++st == KV_STAGES) {
-          st = 0;
-          ph ^= 1;
+  // item i of this CTA -> (window b, head h, query pair qb); consecutive items share K/V through L2
+  auto item_coords = [&](int it, int& b, int& h, int& qb) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    qb = item % qpairs;
+    const int bh = item / qpairs;
+    h = bh % HEADS;
+    b = bh / HEADS;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      uint32_t g = 0;  // running K/V block number
+      for (int it = 0; it < my_items; ++it) {
+        int b, h, qb;
+        item_coords(it, b, h, qb);
+        const int row_base = b * tokens;
+        const int qs = it & 1;
+        if (it >= 2) mbar_wait(&q_empty[qs], ((it >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&q_full[qs], QTILES * TILE_BYTES);
+        for (int t = 0; t < QTILES; ++t)
+          tma_load_2d(smem + OFF_Q + (qs * QTILES + t) * TILE_BYTES, &tm, &q_full[qs], h * D,
+                      row_base + (qb * QTILES + t) * BQ);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const uint32_t stg = g % KV_STAGES;
+          if (g >= (uint32_t)KV_STAGES) mbar_wait(&kv_empty[stg], ((g / KV_STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&kv_full[stg], 2 * TILE_BYTES);
+          uint8_t* dst = smem + OFF_KV + stg * 2 * TILE_BYTES;
+          tma_load_2d(dst, &tm, &kv_full[stg], HID + h * D, row_base + j * BKV);
+          tma_load_2d(dst + TILE_BYTES, &tm, &kv_full[stg], 2 * HID + h * D, row_base + j * BKV);
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t sp = smem_u32(smem + OFF_P);
-      auto kv_addr = [&](int j) { return smem_u32(smem + OFF_KV + (j % KV_STAGES) * 2 * TILE_BYTES); };
-      auto issue_s = [&](int t, int j) {  // S_t = Q_t K_j^T
-        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + OFF_Q + t * TILE_BYTES), 16, 1024);
-        const uint64_t k_desc = umma_desc_sw128(kv_addr(j), 16, 1024);
+    } else if (warp == 1 || warp == 2) {
+      // ------------------------------------------------------------------ MMA issuers: warp 1 = tile A, warp 2 = tile B
+      // Per tile the events arrive in a fixed order (S buffer read -> P published), so each issuer simply blocks on
+      // its next mbarrier (a suspended try_wait costs no issue slots; a polling loop over both tiles' barriers
+      // starved the two softmax warps that share its scheduler).  The whole warp walks the loop on warp-uniform
+      // state and one elected lane issues: under a divergent `lane == 0` ptxas wraps every UTCHMMA in an
+      // ELECT / BRA.U.ANY loop, ~90 clk per instruction against 32-64 clk of tensor work.
+      const int t = warp - 1;
+      const uint32_t G = (uint32_t)my_items * (uint32_t)nkv;  // key blocks of this tile over all items of this CTA
+      const uint32_t d_s = tmem_base + TM_S + t * BKV, d_o = tmem_base + TM_O + t * D, a_p = tmem_base + TM_P + t * 64;
+      auto issue_s = [&](uint32_t g) {  // S_t(g) = Q_t K_g^T; K/V stage g and the Q buffer of its item are full
+        const uint32_t it = g / (uint32_t)nkv, j = g - it * (uint32_t)nkv;
+        mbar_wait(&kv_full[g % KV_STAGES], (g / KV_STAGES) & 1);
+        if (j == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + OFF_Q + ((it & 1) * QTILES + t) * TILE_BYTES), 16, 1024);
+          const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + OFF_KV + (g % KV_STAGES) * 2 * TILE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16_ss(tmem_base + TM_S + t * BKV, q_desc + 2 * k, k_desc + 2 * k, IDESC_S, k != 0);
-        umma_commit(&s_full[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      // Tile B starts one softmax period after tile A (stagger): two softmax groups that start together slow each
-      // other down symmetrically on the shared MUFU pipe and then idle together while the tensor core produces
-      // their next scores; half a period apart, one group's MUFU phase covers the other's wait for S.
-      issue_s(0, 0);
-      if (!stagger) issue_s(1, 0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {  // K_{j+1} / V_{j+1} must have landed before the first S_t(j+1)
-          mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-          tc_fence_after();
+          for (int k = 0; k < D / 16; ++k) umma_bf16_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, IDESC_S, k != 0);
+          umma_commit(&s_full[t]);
+          // the Q buffer of the item is dead once the last S of both tiles has executed (barrier count 2)
+          if (j == (uint32_t)nkv - 1) umma_commit(&q_empty[it & 1]);
+          if (tr && t == 0 && g < 15) tr[8 + g * 8 + 5] = clock64();
         }
-        const uint32_t sv = kv_addr(j) + TILE_BYTES;
-        for (int t = 0; t < QTILES; ++t) {
-          mbar_wait(&p_full[t], j & 1);  // P_t(j) is in smem and S_t(j) has been read out of TMEM
-          tc_fence_after();
-          if (tr && t == 0) tr[8 + j * 8 + 4] = clock64();
-          if (j + 1 < nkv) issue_s(t, j + 1);
-          if (tr && t == 0) tr[8 + j * 8 + 5] = clock64();
-          const uint32_t d_o = tmem_base + TM_O + t * D;
+        __syncwarp();
+      };
+      // Tile B starts a fraction of a block period after tile A so that the two softmax groups do not need the MUFU
+      // pipe at the same time (stagger 1: once A has pulled its first scores out of TMEM, 2: once A published P(0)).
+      if (G > 0 && t == 1 && stagger == 1) mbar_wait(&s_free[0], 0);
+      if (G > 0 && t == 1 && stagger == 2) mbar_wait(&p_full[0], 0);
+      if (G > 0) issue_s(0);
+      for (uint32_t g = 0; g < G; ++g) {
+        if (g + 1 < G) {
+          mbar_wait(&s_free[t], g & 1);  // the softmax warps hold S(g) in registers: the buffer can take S(g+1)
+          issue_s(g + 1);
+        }
+        mbar_wait(&p_full[t], g & 1);    // P(g) is in TMEM
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t j = g % (uint32_t)nkv;
+          const uint32_t sv = smem_u32(smem + OFF_KV + (g % KV_STAGES) * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
-            // A = P_t: two 64-key swizzle atoms of 16 KiB; B = V_j: 16 keys = 16 rows of 128 B (MN-major)
-            const uint64_t p_desc = umma_desc_sw128(sp + t * P_BYTES + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
+            // A = P_t: 16 keys = 8 TMEM columns; B = V_j: 16 keys = 16 rows of 128 B (MN-major)
             const uint64_t v_desc = umma_desc_sw128(sv + k * 16 * 128, 1024, 1024);
-            umma_bf16_ss(d_o, p_desc, v_desc, IDESC_O, (j | k) != 0);
+            umma_bf16_ts(d_o, a_p + k * 8, v_desc, IDESC_O, (j | (uint32_t)k) != 0);
           }
           umma_commit(&pv_done[t]);
-          if (tr && t == 0) tr[8 + j * 8 + 6] = clock64();
-          if (stagger && j == 0 && t == 0) issue_s(1, 0);
+          umma_commit(&kv_empty[g % KV_STAGES]);  // K_g / V_g are dead once both tiles' P V have executed (count 2)
+          if (tr && t == 0 && g < 15) tr[8 + g * 8 + 6] = clock64();
         }
-        umma_commit(&kv_empty[j % KV_STAGES]);  // K_j and V_j are dead once both tiles' P V products have executed
+        __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
+    // ------------------------------------------------------------------ softmax + epilogue
     const int t = (warp - 4) >> 2;       // query tile of this warp group
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t t_s = t_lane + TM_S + t * BKV, t_o = t_lane + TM_O + t * D;
-    const uint32_t sp_row = smem_u32(smem + OFF_P + t * P_BYTES) + row * 128;
+    const uint32_t t_s = t_lane + TM_S + t * BKV, t_o = t_lane + TM_O + t * D, t_p = t_lane + TM_P + t * 64;
     const bool tracer = tr && warp == 4 && lane == 0;
-    float m = -INFINITY;
-    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
-
-    for (int j = 0; j < nkv; ++j) {
-      if (tracer) tr[8 + j * 8 + 0] = clock64();
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      if (tracer) tr[8 + j * 8 + 1] = clock64();
-      const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
-      if (kmax < BKV)
-        softmax_block<true, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b, tracer ? tr + 8 + j * 8 : nullptr);
-      else
-        softmax_block<false, POLY>(j, kmax, t_s, t_o, sp_row, row, &pv_done[t], m, l2a, l2b, tracer ? tr + 8 + j * 8 : nullptr);
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(&p_full[t]);
-      if (tracer) tr[8 + j * 8 + 2] = clock64();
-    }
-    if (tracer) tr[2] = clock64();
-    {
-      const int jl = nkv - 1;
-      mbar_wait(&pv_done[t], jl & 1);
-      tc_fence_after();
-      const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
-      const int q = (qb * QTILES + t) * BQ + row;
-      __nv_bfloat16* dst = out + (long long)(row_base + q) * HID + h * D;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_o + c * 32, r);
-        tmem_ld_wait();
-        if (q < tokens) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = v;
-          }
+    SoftmaxState st;
+    st.m = -INFINITY;
+    st.l2a = make_float2(0.f, 0.f);
+    st.l2b = make_float2(0.f, 0.f);
+    uint32_t n = 0;  // running key-block number of this tile
+    for (int it = 0; it < my_items; ++it) {
+      int b, h, qb;
+      item_coords(it, b, h, qb);
+      for (int j = 0; j < nkv; ++j, ++n) {
+        long long* trj = (tracer && n < 15) ? tr + 8 + n * 8 : nullptr;
+        if (trj) trj[0] = clock64();
+        mbar_wait(&s_full[t], n & 1);
+        tc_fence_after();
+        if (trj) trj[1] = clock64();
+        const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
+        if (kmax < BKV) {
+          if (j == 0)
+            softmax_block<true, true, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+          else
+            softmax_block<true, false, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+        } else {
+          if (j == 0)
+            softmax_block<false, true, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+          else
+            softmax_block<false, false, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         }
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        if (trj) trj[2] = clock64();
       }
+      // epilogue of the item: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store per tile (rows beyond the
+      // window's last token are clipped by the 3-D tensor map).  The next item's first P V (accumulate = 0) is only
+      // issued after this thread has published its next P, i.e. after these TMEM reads.
+      mbar_wait(&pv_done[t], (n - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / ((st.l2a.x + st.l2a.y) + (st.l2b.x + st.l2b.y));
+      uint32_t r[64];
+      tmem_ld32_at<0>(t_o, r);
+      tmem_ld32_at<32>(t_o + 32, r);
+      tmem_ld_wait();
+      const bool leader = (warp & 3) == 0 && lane == 0;
+      if (leader) bulk_wait_read0();  // the previous item's store has finished reading the staging tile
+      named_bar_sync(1 + t, 128);
+      uint8_t* stg = smem + OFF_STG + t * TILE_BYTES;
+      const uint32_t stg_row = smem_u32(stg) + row * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        st_shared_v4(stg_row + ((uint32_t)(g ^ (row & 7)) << 4),
+                     pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv),
+                     pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv),
+                     pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv),
+                     pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv));
+      fence_proxy_async();
+      named_bar_sync(1 + t, 128);
+      if (leader) {
+        tma_store_3d(&tm_out, stg, h * D, (qb * QTILES + t) * BQ, b);
+        bulk_commit();
+      }
+      if (tracer && it == 0) tr[2] = clock64();
     }
+    if ((warp & 3) == 0 && lane == 0) bulk_wait0();  // every output tile has landed before the CTA retires
   }
   __syncwarp();
   tc_fence_before();
@@ -340,15 +444,17 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
     set_error("attention_bf16: null pointer or empty shape");
     return ZK_ERR_ARG;
   }
-  if (batch > 65535) {
-    set_error("attention_bf16: batch %d > 65535", batch);
+  const int qpairs = (tokens + QTILES * BQ - 1) / (QTILES * BQ);
+  const long long items = (long long)qpairs * HEADS * batch;
+  if (items > 0x7fffffffLL || (long long)batch * tokens > 0x7fffffffLL) {
+    set_error("attention_bf16: batch %d x tokens %d is too large", batch, tokens);
     return ZK_ERR_SHAPE;
   }
   static int poly = -1;  // share of exp2 evaluated on the FMA pipe: 0, 1 or 2 of every 4 pairs (ZK_ATTN_POLY overrides)
   static int stagger = 1;
   if (poly < 0) {
     const char* sg = getenv("ZK_ATTN_STAGGER");
-    if (sg) stagger = atoi(sg) != 0;
+    if (sg) stagger = atoi(sg);
     ZK_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ZK_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ZK_CUDA(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -358,14 +464,16 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
   }
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
-  dim3 grid((tokens + QTILES * BQ - 1) / (QTILES * BQ), HEADS, batch);
+  const int grid = items < num_sms() ? (int)items : num_sms();
+  CUtensorMap o;
+  if ((rc = make_tmap_bf16_3d(&o, out, (uint64_t)batch, (uint64_t)tokens, HID, HID, (uint64_t)tokens * HID, 128, 64))) return rc;
   ProfScope prof(ZK_K_ATTENTION, stream);
   if (poly == 0)
-    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, stagger, trace);
+    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
   else if (poly == 1)
-    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, stagger, trace);
+    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
   else
-    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), tokens, stagger, trace);
+    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
 }

@@ -65,6 +65,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is still pending).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C ABI),
 // never as a hung GPU.  ~4 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -104,6 +116,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // TMA tile reduction: global[tile] += shared[tile] (element type from the tensor map; one writer per element here).
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -251,6 +272,10 @@ int num_sms();
 // box_cols must be 64 (128 B); box_rows <= 256.  Out-of-bounds rows/cols are zero filled.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// bf16 [slabs][rows][cols] (row pitch / slab pitch in elements), (1 x box_rows x 64) box, 128-B swizzle: rows beyond
+// `rows` are clipped per slab, so a tile that overhangs the end of one slab never touches the next one.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t slabs, uint64_t rows, uint64_t cols,
+                      uint64_t pitch_elems, uint64_t slab_pitch_elems, uint32_t box_rows, uint32_t box_cols);
 // same for fp32 (box_cols must be 32 = 128 B)
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                      uint32_t box_rows, uint32_t box_cols);

@@ -153,19 +153,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-        const int acc = t & 1;
-        const uint32_t acc_phase = (t >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // The whole warp walks the pipeline on warp-uniform state and one elected lane issues: under a divergent
+    // `lane == 0` ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~90 clk per instruction).
+    int stage = 0;
+    uint32_t phase = 0;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
@@ -174,12 +176,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == kblocks - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
