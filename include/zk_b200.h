@@ -193,7 +193,7 @@ int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, in
 enum zk_kernel_class {
   ZK_K_RESAMPLE = 0, ZK_K_FBANK = 1, ZK_K_GATHER = 2, ZK_K_GEMM_PATCH = 3, ZK_K_LAYERNORM = 4,
   ZK_K_GEMM_QKV = 5, ZK_K_ATTENTION = 6, ZK_K_GEMM_OUT = 7, ZK_K_GEMM_FC1 = 8, ZK_K_GEMM_FC2 = 9,
-  ZK_K_HEAD = 10, ZK_K_GATE = 11, ZK_K_MISC = 12, ZK_K_NUM_CLASSES = 13
+  ZK_K_HEAD = 10, ZK_K_GATE = 11, ZK_K_MISC = 12, ZK_K_TAIL = 13, ZK_K_NUM_CLASSES = 14
 };
 void zk_prof_enable(int time_launches);
 /* ms[ZK_K_NUM_CLASSES] (0 where timing was off), launches[ZK_K_NUM_CLASSES]; returns 0 or a cudaError_t */

@@ -101,3 +101,21 @@ def test_fused_fbank_path_matches_contract_path():
     idx = torch.tensor([5, 2, 9], dtype=torch.int32, device="cuda")
     c = m.forward_fbank(fb, 3, synth.STAGE1_MEAN, synth.STAGE1_STD, window_index=idx)
     assert torch.equal(c, a[idx.long()])
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_last_layer_tail_matches_full_layer(batch):
+    """The pruned last layer (K/V for every token, everything else for tokens 0/1 only) must give the logits of the
+    full layer: same inputs, same bf16 operands; only the 2-query attention runs in fp32 instead of bf16 P."""
+    from zenker_audio_detection_b200 import ops, synth
+
+    sd = synth.random_state_dict(9)
+    plan = ops.FbankPlan()
+    w = torch.from_numpy(synth.cfg1_windows(8)[:batch]).cuda()
+    feats = plan.fx_contract(w, synth.STAGE1_MEAN, synth.STAGE1_STD, 1024)
+    for layers in (1, 12):
+        m = ops.AstModel(sd, num_layers=layers)
+        pruned = m.forward_features(feats)
+        full, _ = m.forward_features(feats, return_hidden=True)  # asking for the hidden state forces the full layer
+        err = (pruned - full).abs().max().item()
+        assert err <= 4e-3, (layers, err)

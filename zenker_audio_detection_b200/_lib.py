@@ -81,7 +81,7 @@ SIGNATURES = {
     "zk_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zk_kernel_class_name": (C.c_char_p, [C.c_int]),
 }
-NUM_KERNEL_CLASSES = 13
+NUM_KERNEL_CLASSES = 14
 
 
 def prof_enable(time_launches: bool) -> None:

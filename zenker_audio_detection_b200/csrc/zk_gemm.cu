@@ -290,7 +290,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 }  // namespace gemm
 
 int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long long M, int N, int K, int epilogue,
-              const float* aux, int aux_rows, cudaStream_t stream) {
+              const float* aux, int aux_rows, cudaStream_t stream, long long out_pitch, int prof_cls) {
   using namespace gemm;
   int rc = device_check();
   if (rc) return rc;
@@ -306,13 +306,18 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
     set_error("gemm_bf16: ZK_EPI_PATCH_F32 needs the position table and patches per window");
     return ZK_ERR_ARG;
   }
+  if (out_pitch <= 0) out_pitch = N;
+  if (out_pitch < N || (epilogue == ZK_EPI_PATCH_F32 && out_pitch != N)) {
+    set_error("gemm_bf16: output pitch %lld < N %d", out_pitch, N);
+    return ZK_ERR_SHAPE;
+  }
   CUtensorMap tmA, tmB, tmC;
   if ((rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, BK))) return rc;
   if (epilogue == ZK_EPI_BIAS_BF16 || epilogue == ZK_EPI_BIAS_GELU_BF16) {
-    if ((rc = make_tmap_bf16_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)out_pitch, 32, 64))) return rc;
   } else if (epilogue == ZK_EPI_BIAS_RESID_F32) {
-    if ((rc = make_tmap_f32_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 32))) return rc;
+    if ((rc = make_tmap_f32_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)out_pitch, 32, 32))) return rc;
   } else {
     tmC = tmA;  // unused by the patch epilogue
   }
@@ -326,11 +331,13 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   p.aux_rows = aux_rows;
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
+  const auto cls = [&](int by_epilogue) { return prof_cls >= 0 ? prof_cls : by_epilogue; };
   switch (epilogue) {
-    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, ZK_K_GEMM_QKV, stream);
-    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, ZK_K_GEMM_FC1, stream);
-    case ZK_EPI_BIAS_RESID_F32: return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT, stream);
-    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, tmC, p, ZK_K_GEMM_PATCH, stream);
+    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
+    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
+    case ZK_EPI_BIAS_RESID_F32:
+      return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, cls(K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT), stream);
+    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_PATCH), stream);
   }
   set_error("gemm_bf16: unknown epilogue %d", epilogue);
   return ZK_ERR_ARG;
@@ -340,5 +347,5 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
 
 extern "C" int zk_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int64_t M, int N, int K,
                             int epilogue, const float* d_aux, int aux_rows, zk_stream_t stream) {
-  return zk::gemm_bf16(d_a, d_w, d_bias, d_out, M, N, K, epilogue, d_aux, aux_rows, (cudaStream_t)stream);
+  return zk::gemm_bf16(d_a, d_w, d_bias, d_out, M, N, K, epilogue, d_aux, aux_rows, (cudaStream_t)stream, 0, -1);
 }

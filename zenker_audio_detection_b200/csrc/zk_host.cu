@@ -197,7 +197,7 @@ int zk_prof_collect(float* ms, int64_t* launches) {
 const char* zk_kernel_class_name(int cls) {
   static const char* names[ZK_K_NUM_CLASSES] = {"resample", "fbank", "gather_patches", "gemm_patch", "layernorm",
                                                "gemm_qkv", "attention", "gemm_out", "gemm_fc1", "gemm_fc2",
-                                               "head", "gate", "misc"};
+                                               "head", "gate", "misc", "last_layer_tail"};
   return (cls >= 0 && cls < ZK_K_NUM_CLASSES) ? names[cls] : "?";
 }
 

@@ -9,6 +9,7 @@
 //   mlp  bf16 [B*T][3072]  GELU(fc1) output; its head doubles as the patch-gather matrix [B*P][256]
 // Per layer: LN -> QKV GEMM(+bias) -> attention -> out-proj GEMM(+bias +residual) -> LN -> fc1 GEMM(+bias, GELU)
 //            -> fc2 GEMM(+bias +residual).   LayerNorm, softmax, GELU and all accumulation are fp32.
+#include <stdlib.h>
 #include <string.h>
 
 #include "zk_b200.h"
@@ -123,7 +124,13 @@ static int forward_impl(zk_model* m, const GatherSrc& src, int batch, void* work
   if ((rc = gemm_bf16(ws.mlp, m->patch_w, m->patch_b, ws.x, prow, HID, PATCH_K, ZK_EPI_PATCH_F32, m->pos, m->patches, stream)))
     return rc;
   if ((rc = write_special_tokens(m->cls, m->dist, m->pos, ws.x, batch, m->tokens, stream))) return rc;
-  for (int l = 0; l < m->num_layers; ++l) {
+  // The classifier reads tokens 0 and 1 of the last hidden state only, so unless the caller asked for the full hidden
+  // state the last layer runs K/V for every token and everything else for those two rows per window (identical
+  // logits, 7.2 % fewer flops: 242.2 of 261.0 GFLOP per window are executed).  ZK_FULL_LAST_LAYER=1 disables it.
+  static const bool full_last = getenv("ZK_FULL_LAST_LAYER") && atoi(getenv("ZK_FULL_LAST_LAYER")) != 0;
+  const bool prune = !hidden && !full_last && m->num_layers >= 1;
+  const int full_layers = prune ? m->num_layers - 1 : m->num_layers;
+  for (int l = 0; l < full_layers; ++l) {
     const LayerDev& L = m->layer[l];
     if ((rc = layernorm_bf16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, stream))) return rc;
     if ((rc = gemm_bf16(ws.h, L.qkv_w, L.qkv_b, ws.qkv, rows, QKV, HID, ZK_EPI_BIAS_BF16, nullptr, 0, stream))) return rc;
@@ -133,9 +140,36 @@ static int forward_impl(zk_model* m, const GatherSrc& src, int batch, void* work
     if ((rc = gemm_bf16(ws.h, L.fc1_w, L.fc1_b, ws.mlp, rows, MLP, HID, ZK_EPI_BIAS_GELU_BF16, nullptr, 0, stream))) return rc;
     if ((rc = gemm_bf16(ws.mlp, L.fc2_w, L.fc2_b, ws.x, rows, HID, MLP, ZK_EPI_BIAS_RESID_F32, nullptr, 0, stream))) return rc;
   }
-  if (hidden) ZK_CUDA(cudaMemcpyAsync(hidden, ws.x, (size_t)rows * HID * 4, cudaMemcpyDeviceToDevice, stream));
-  return head_logits(ws.x, batch, m->tokens, m->fln_w, m->fln_b, m->hln_w, m->hln_b, m->head_w, m->head_b, m->num_labels,
-                     m->ln_eps, logits, stream);
+  if (!prune) {
+    if (hidden) ZK_CUDA(cudaMemcpyAsync(hidden, ws.x, (size_t)rows * HID * 4, cudaMemcpyDeviceToDevice, stream));
+    return head_logits(ws.x, batch, m->tokens, m->fln_w, m->fln_b, m->hln_w, m->hln_b, m->head_w, m->head_b,
+                       m->num_labels, m->ln_eps, logits, stream);
+  }
+  {
+    const LayerDev& L = m->layer[m->num_layers - 1];
+    const long long r2 = 2LL * batch;
+    // compact buffers of the two head rows per window live in the (otherwise idle) fc1 activation buffer
+    Carver c{reinterpret_cast<uint8_t*>(ws.mlp), 0};
+    __nv_bfloat16* hq = c.take<__nv_bfloat16>((size_t)r2 * HID);    // LN1 rows, later LN2 rows
+    __nv_bfloat16* q2 = c.take<__nv_bfloat16>((size_t)r2 * HID);    // queries, later the attention output
+    __nv_bfloat16* att2 = c.take<__nv_bfloat16>((size_t)r2 * HID);
+    __nv_bfloat16* mlp2 = c.take<__nv_bfloat16>((size_t)r2 * MLP);
+    float* x2 = c.take<float>((size_t)r2 * HID);
+    if ((rc = layernorm_bf16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, stream))) return rc;
+    // K | V projections of every token, written in place into columns [768, 2304) of the fused QKV buffer
+    if ((rc = gemm_bf16(ws.h, L.qkv_w + (size_t)HID * HID, L.qkv_b + HID, ws.qkv + HID, rows, 2 * HID, HID, ZK_EPI_BIAS_BF16,
+                        nullptr, 0, stream, QKV, ZK_K_GEMM_QKV)))
+      return rc;
+    if ((rc = gather_head_rows(ws.h, ws.x, batch, m->tokens, hq, x2, stream))) return rc;
+    if ((rc = gemm_bf16(hq, L.qkv_w, L.qkv_b, q2, r2, HID, HID, ZK_EPI_BIAS_BF16, nullptr, 0, stream, 0, ZK_K_TAIL))) return rc;
+    if ((rc = attention_head_rows(q2, ws.qkv, att2, batch, m->tokens, stream))) return rc;
+    if ((rc = gemm_bf16(att2, L.o_w, L.o_b, x2, r2, HID, HID, ZK_EPI_BIAS_RESID_F32, nullptr, 0, stream, 0, ZK_K_TAIL))) return rc;
+    if ((rc = layernorm_bf16_cls(x2, L.ln2_w, L.ln2_b, m->ln_eps, hq, r2, HID, ZK_K_TAIL, stream))) return rc;
+    if ((rc = gemm_bf16(hq, L.fc1_w, L.fc1_b, mlp2, r2, MLP, HID, ZK_EPI_BIAS_GELU_BF16, nullptr, 0, stream, 0, ZK_K_TAIL))) return rc;
+    if ((rc = gemm_bf16(mlp2, L.fc2_w, L.fc2_b, x2, r2, HID, MLP, ZK_EPI_BIAS_RESID_F32, nullptr, 0, stream, 0, ZK_K_TAIL))) return rc;
+    return head_logits(x2, batch, 2, m->fln_w, m->fln_b, m->hln_w, m->hln_b, m->head_w, m->head_b, m->num_labels, m->ln_eps,
+                       logits, stream);
+  }
 }
 
 }  // namespace zk

@@ -88,6 +88,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 int layernorm_bf16(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols,
                    cudaStream_t stream) {
+  return layernorm_bf16_cls(x, w, b, eps, out, rows, cols, ZK_K_LAYERNORM, stream);
+}
+
+int layernorm_bf16_cls(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols,
+                       int prof_cls, cudaStream_t stream) {
   if (!x || !w || !b || !out || rows <= 0) {
     set_error("layernorm_bf16: bad arguments");
     return ZK_ERR_ARG;
@@ -98,9 +103,138 @@ int layernorm_bf16(const float* x, const float* w, const float* b, float eps, vo
   }
   long long blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  ProfScope prof(ZK_K_LAYERNORM, stream);
+  ProfScope prof(prof_cls, stream);
   layernorm_kernel<<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
   ZK_LAUNCH_CHECK("layernorm_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ last-layer tail
+// Only tokens 0 (cls) and 1 (distillation) of the last hidden state reach the classifier (HF:modeling...:378-380,
+// 388-394), so in the last encoder layer every per-token operation after the K/V projection is needed for those two
+// rows of each window only.  gather_head_rows compacts them; attention_head_rows is the same softmax(q K^T / 8) V as
+// the fused kernel, for two queries per (window, head), in fp32 on the CUDA cores (0.1 % of a layer's flops).
+__global__ void __launch_bounds__(192) gather_head_rows_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ x,
+                                                               int tokens, __nv_bfloat16* __restrict__ hq,
+                                                               float* __restrict__ x2) {
+  const int r = blockIdx.x;  // compact row 2 b + tok
+  const long long src = (long long)(r >> 1) * tokens + (r & 1);
+  const int c = threadIdx.x * 4;
+  *reinterpret_cast<uint2*>(hq + (long long)r * LN_COLS + c) = *reinterpret_cast<const uint2*>(h + src * LN_COLS + c);
+  *reinterpret_cast<float4*>(x2 + (long long)r * LN_COLS + c) = *reinterpret_cast<const float4*>(x + src * LN_COLS + c);
+}
+
+int gather_head_rows(const void* h, const float* x, int batch, int tokens, void* hq, float* x2, cudaStream_t stream) {
+  ProfScope prof(ZK_K_TAIL, stream);
+  gather_head_rows_kernel<<<2 * batch, 192, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h), x, tokens,
+                                                         reinterpret_cast<__nv_bfloat16*>(hq), x2);
+  ZK_LAUNCH_CHECK("gather_head_rows_kernel");
+  return 0;
+}
+
+constexpr int AH_THREADS = 256, AH_HEADS = 12, AH_D = 64, AH_QKV = 3 * LN_COLS;
+__global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const __nv_bfloat16* __restrict__ q2,
+                                                                         const __nv_bfloat16* __restrict__ qkv,
+                                                                         __nv_bfloat16* __restrict__ out2, int tokens) {
+  extern __shared__ float ah_sm[];  // scores [2][tokens], then q [2][64], reduction scratch
+  float* sc = ah_sm;
+  float* qs = ah_sm + 2 * tokens;
+  float* red = qs + 2 * AH_D;       // [2][8] warp partials, later [2][2][64] partial outputs
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
+  if (tid < 2 * AH_D)
+    qs[tid] = __bfloat162float(q2[(long long)(2 * b + (tid >> 6)) * LN_COLS + h * AH_D + (tid & 63)]) * SCALE_LOG2E;
+  __syncthreads();
+  const __nv_bfloat16* kbase = qkv + (long long)b * tokens * AH_QKV + LN_COLS + h * AH_D;
+  const __nv_bfloat16* vbase = kbase + LN_COLS;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int key = tid; key < tokens; key += AH_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * AH_QKV);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = __ldg(kr + i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+        const int d = i * 8 + j * 2;
+        d0 = fmaf(lo, qs[d], fmaf(hi, qs[d + 1], d0));
+        d1 = fmaf(lo, qs[AH_D + d], fmaf(hi, qs[AH_D + d + 1], d1));
+      }
+    }
+    sc[key] = d0;
+    sc[tokens + key] = d1;
+    m0 = fmaxf(m0, d0);
+    m1 = fmaxf(m1, d1);
+  }
+  m0 = warp_max(m0);
+  m1 = warp_max(m1);
+  if (lane == 0) {
+    red[warp] = m0;
+    red[8 + warp] = m1;
+  }
+  __syncthreads();
+  m0 = red[0];
+  m1 = red[8];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    m0 = fmaxf(m0, red[i]);
+    m1 = fmaxf(m1, red[8 + i]);
+  }
+  __syncthreads();
+  float l0 = 0.f, l1 = 0.f;
+  for (int key = tid; key < tokens; key += AH_THREADS) {
+    const float p0 = exp2f(sc[key] - m0), p1 = exp2f(sc[tokens + key] - m1);
+    sc[key] = p0;
+    sc[tokens + key] = p1;
+    l0 += p0;
+    l1 += p1;
+  }
+  l0 = warp_sum(l0);
+  l1 = warp_sum(l1);
+  if (lane == 0) {
+    red[warp] = l0;
+    red[8 + warp] = l1;
+  }
+  __syncthreads();
+  l0 = 0.f;
+  l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    l0 += red[i];
+    l1 += red[8 + i];
+  }
+  __syncthreads();
+  // o[qi][d] = sum_key p[qi][key] V[key][d]: thread = (key half, query, dim); a warp reads 64-byte runs of V rows
+  const int d = tid & 63, qi = (tid >> 6) & 1, half = tid >> 7;
+  const float* pr = sc + qi * tokens;
+  float acc = 0.f;
+  for (int key = half; key < tokens; key += 2) acc = fmaf(pr[key], __bfloat162float(vbase[(long long)key * AH_QKV + d]), acc);
+  red[(half * 2 + qi) * AH_D + d] = acc;
+  __syncthreads();
+  if (tid < 2 * AH_D) {
+    const float o = (red[qi * AH_D + d] + red[(2 + qi) * AH_D + d]) / (qi ? l1 : l0);
+    out2[(long long)(2 * b + qi) * LN_COLS + h * AH_D + d] = __float2bfloat16(o);
+  }
+}
+
+int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, int tokens, cudaStream_t stream) {
+  const size_t smem = (size_t)(2 * tokens + 2 * AH_D + 4 * AH_D) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("attention_head_rows: %d tokens do not fit the score buffer", tokens);
+    return ZK_ERR_SHAPE;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZK_CUDA(cudaFuncSetAttribute(attention_head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  ProfScope prof(ZK_K_TAIL, stream);
+  attention_head_rows_kernel<<<dim3(AH_HEADS, batch), AH_THREADS, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q2), reinterpret_cast<const __nv_bfloat16*>(qkv),
+      reinterpret_cast<__nv_bfloat16*>(out2), tokens);
+  ZK_LAUNCH_CHECK("attention_head_rows_kernel");
   return 0;
 }
 
