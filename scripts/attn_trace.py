@@ -29,7 +29,7 @@ for c in range(2):
     print(f"CTA {c} on SM {t[c,0]}: first item done at +{t[c,2]-t0}")
     for n in range(15):
         r = t[c, 8 + 8 * n: 16 + 8 * n] - t0
-        print(f"   n={n:2d}: S issued {r[5]:7d} | wait {r[0]:7d} S_ready {r[1]:7d} (+{r[1]-r[0]:5d}) loaded {r[3]-r[1]:5d} max {r[7]-r[3]:5d} exp+store {r[2]-r[7]:5d} -> P_pub {r[2]:7d} | PV issued {r[6]:7d} (+{r[6]-r[2]:4d})")
+        print(f"   n={n:2d}: S issued {r[5]:7d} | wait {r[0]:7d} S_ready {r[1]:7d} (+{r[1]-r[0]:5d}) loaded {r[3]-r[1]:5d} max {r[7]-r[3]:5d} exp+store {r[2]-r[7]:5d} -> P_pub {r[2]:7d} | PV issued {r[6]:7d} (+{r[6]-r[2]:4d}) | tile B P_pub {r[4]:7d} (A{r[4]-r[2]:+6d})")
 d = []
 for c in range(ncta):
     for n in range(2, 14):

@@ -395,6 +395,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         tc_fence_before();
         mbar_arrive(&p_full[t]);
         if (trj) trj[2] = clock64();
+        if (tr && warp == 8 && lane == 0 && n < 15) tr[8 + n * 8 + 4] = clock64();  // tile B: P published
       }
       // epilogue of the item: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store per tile (rows beyond the
       // window's last token are clipped by the 3-D tensor map).  The next item's first P V (accumulate = 0) is only

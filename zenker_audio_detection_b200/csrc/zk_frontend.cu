@@ -10,6 +10,8 @@
 // bin instead of the reference's dense 257x128 matmul), log, and the optional (x-mean)/(2 std).
 #include <string.h>
 
+#include <type_traits>
+
 #include "zk_b200.h"
 #include "zk_common.cuh"
 #include "zk_fbank_math.cuh"
@@ -223,28 +225,71 @@ __device__ __forceinline__ float load_mean<int16_t>(const int16_t* in, long long
   return __fdiv_rn(a, (float)channels);
 }
 
+// Persistent CTAs walk tiles of OB = 256 R outputs.  The ORIG*OB + KLEN inputs of a tile are staged in shared memory
+// by ONE 1-D bulk async copy (UBLKCP, the TMA engine) on an mbarrier, issued one tile ahead into the other buffer, so
+// HBM reads are 21 KiB bursts that overlap the FIR of the current tile; boundary tiles, multi-channel and PCM16
+// sources take a guarded coalesced load instead (channel mean / 2^-15 scaling fused there).  Each thread produces R
+// consecutive outputs from a register window of (R-1) ORIG + KLEN inputs (thread stride ORIG R floats: odd for
+// 48 kHz -> conflict-free LDS); results go back through shared memory and leave as one bulk store per tile.
+constexpr int DEC_THREADS = 256;
 template <typename T, int ORIG, int WIDTH, int R>
-__global__ void __launch_bounds__(128) decimate_kernel(const T* __restrict__ in, long long n_in, int channels,
-                                                       long long ch_pitch, const float* __restrict__ taps,
-                                                       float* __restrict__ out, long long n_out) {
-  constexpr int KLEN = 2 * WIDTH + ORIG, OB = 128 * R, NIN = OB * ORIG + KLEN, WIN = (R - 1) * ORIG + KLEN;
-  __shared__ float xs[NIN];
-  __shared__ float tp[KLEN];
-  __shared__ float ys[OB];
+__global__ void __launch_bounds__(DEC_THREADS, 2) decimate_kernel(const T* __restrict__ in, long long n_in, int channels,
+                                                                  long long ch_pitch, const float* __restrict__ taps,
+                                                                  float* __restrict__ out, long long n_out, int bulk_ok) {
+  constexpr int KLEN = 2 * WIDTH + ORIG, OB = DEC_THREADS * R, WIN = (R - 1) * ORIG + KLEN;
+  constexpr int PAD = (4 - WIDTH % 4) % 4;                       // tile source starts at a multiple of 4 floats
+  constexpr int NIN = (ORIG * (OB - 1) + PAD + KLEN + 3) / 4 * 4;  // floats staged per tile
+  static_assert((ORIG * OB) % 4 == 0 && OB % 4 == 0, "16-byte aligned tiles");
+  extern __shared__ __align__(16) float dsm[];
+  float* xs0 = dsm;                 // [2][NIN]
+  float* ys = dsm + 2 * NIN;        // [OB]
+  float* tp = ys + OB;              // [KLEN]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tp + (KLEN + 1) / 2 * 2);  // [2]
   const int tid = threadIdx.x;
-  if (tid < KLEN) tp[tid] = taps[tid];
-  for (long long blk = blockIdx.x; blk * OB < n_out; blk += gridDim.x) {
-    const long long o0 = blk * OB;
-    const long long g0 = o0 * ORIG - WIDTH;
-    __syncthreads();
-    for (int i = tid; i < NIN; i += 128) {
+  for (int i = tid; i < KLEN; i += DEC_THREADS) tp[i] = taps[i];
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long num_tiles = (n_out + OB - 1) / OB;
+  // stage tile `tile` into buffer `b`: returns true when it was issued as an asynchronous bulk copy
+  auto stage = [&](long long tile, int b) -> bool {
+    float* xs = xs0 + b * NIN;
+    const long long g0 = tile * OB * ORIG - WIDTH - PAD;
+    if (bulk_ok && g0 >= 0 && g0 + NIN <= n_in) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bar[b], NIN * 4);
+        bulk_load_1d(xs, reinterpret_cast<const float*>(in) + g0, NIN * 4, &bar[b]);
+      }
+      return true;
+    }
+    for (int i = tid; i < NIN; i += DEC_THREADS) {
       const long long g = g0 + i;
       xs[i] = (g >= 0 && g < n_in) ? load_mean<T>(in, g, channels, ch_pitch) : 0.f;
     }
-    __syncthreads();
+    return false;
+  };
+  uint32_t phase[2] = {0, 0};
+  bool async_cur = false;
+  if ((long long)blockIdx.x < num_tiles) async_cur = stage(blockIdx.x, 0);
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    bool async_next = false;
+    if (tile + gridDim.x < num_tiles) async_next = stage(tile + gridDim.x, b ^ 1);  // buffer b^1 was released by the
+                                                                                  // __syncthreads of the last round
+    if (async_cur) {
+      mbar_wait(&bar[b], phase[b]);
+      phase[b] ^= 1;
+    } else {
+      __syncthreads();
+    }
+    const float* xs = xs0 + b * NIN + tid * (R * ORIG) + PAD;
     float xv[WIN];
 #pragma unroll
-    for (int i = 0; i < WIN; ++i) xv[i] = xs[tid * R * ORIG + i];
+    for (int i = 0; i < WIN; ++i) xv[i] = xs[i];
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
@@ -254,12 +299,28 @@ __global__ void __launch_bounds__(128) decimate_kernel(const T* __restrict__ in,
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = fmaf(t, xv[r * ORIG + k], acc[r]);
     }
+    if (tid == 0) bulk_wait_read0();  // the previous tile's bulk store has finished reading ys
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; ++r) ys[tid * R + r] = acc[r];
-    __syncthreads();
-    for (int i = tid; i < OB; i += 128)
-      if (o0 + i < n_out) out[o0 + i] = ys[i];
+    const long long o0 = tile * OB;
+    if (o0 + OB <= n_out && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + o0), "r"(smem_u32(ys)),
+                     "r"(OB * 4)
+                     : "memory");
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < OB; i += DEC_THREADS)
+        if (o0 + i < n_out) out[o0 + i] = ys[i];
+    }
+    async_cur = async_next;
   }
+  if (tid == 0) bulk_wait0();
 }
 
 // Generic ratio: one thread per output sample (any orig/new, e.g. 44.1 kHz -> 16 kHz = 441/160).
@@ -298,14 +359,24 @@ static int run(const T* in, long long n_in, int channels, long long ch_pitch, co
   }
   if (n_out == 0) return 0;
   const int sms = num_sms();
-#define ZK_DECIMATE(O, W, R)                                                                                  \
-  if (new_ == 1 && orig == O && width == W) {                                                                 \
-    long long blocks = (n_out + 128 * R - 1) / (128 * R);                                                      \
-    if (blocks > 8LL * sms) blocks = 8LL * sms;                                                                \
-    ProfScope prof(ZK_K_RESAMPLE, stream);                                                                     \
-    decimate_kernel<T, O, W, R><<<(int)blocks, 128, 0, stream>>>(in, n_in, channels, ch_pitch, taps, out, n_out); \
-    ZK_LAUNCH_CHECK("decimate_kernel");                                                                       \
-    return 0;                                                                                                 \
+#define ZK_DECIMATE(O, W, R)                                                                                   \
+  if (new_ == 1 && orig == O && width == W) {                                                                  \
+    constexpr int KLEN = 2 * W + O, OB = DEC_THREADS * R, PAD = (4 - W % 4) % 4;                                \
+    constexpr int NIN = (O * (OB - 1) + PAD + KLEN + 3) / 4 * 4;                                                \
+    constexpr int SMEM = (2 * NIN + OB + (KLEN + 1) / 2 * 2) * 4 + 16;                                          \
+    static bool attr_done = false;                                                                              \
+    if (!attr_done) {                                                                                           \
+      ZK_CUDA(cudaFuncSetAttribute(decimate_kernel<T, O, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); \
+      attr_done = true;                                                                                         \
+    }                                                                                                           \
+    long long blocks = (n_out + OB - 1) / OB;                                                                   \
+    if (blocks > 2LL * sms) blocks = 2LL * sms;                                                                 \
+    const int bulk_ok = std::is_same<T, float>::value && channels == 1 && (reinterpret_cast<uintptr_t>(in) & 15) == 0; \
+    ProfScope prof(ZK_K_RESAMPLE, stream);                                                                      \
+    decimate_kernel<T, O, W, R><<<(int)blocks, DEC_THREADS, SMEM, stream>>>(in, n_in, channels, ch_pitch, taps, out, \
+                                                                            n_out, bulk_ok);                   \
+    ZK_LAUNCH_CHECK("decimate_kernel");                                                                        \
+    return 0;                                                                                                  \
   }
   ZK_DECIMATE(3, 19, 7)   // 48 kHz -> 16 kHz
   ZK_DECIMATE(2, 13, 7)   // 32 kHz -> 16 kHz
