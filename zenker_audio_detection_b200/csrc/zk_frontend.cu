@@ -1,13 +1,16 @@
 // Audio front end for sm_100a: polyphase resampler and the Kaldi-compatible log-mel filterbank.
 //
-// fbank kernel: persistent CTAs walk tiles of 32 consecutive frames.  The 5360 samples a tile needs are
-// staged into shared memory with ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) that
-// completes on an mbarrier; the copy of tile i+1 is issued before tile i is processed (double buffer), so
-// HBM reads are contiguous 21 KiB bursts and each sample is fetched from HBM once although frames overlap
-// 2.5x.  16 lanes own one frame (two frames per warp): DC removal, pre-emphasis and the window are applied
-// in registers, the 512-point real FFT is a 256-point complex FFT (two in-lane DFT-16 passes around one
-// padded shared-memory transpose), followed by the power spectrum, the sparse mel filterbank (<= 16 taps per
-// bin instead of the reference's dense 257x128 matmul), log, and the optional (x-mean)/(2 std).
+// fbank kernel: one persistent CTA per SM (12 warps) walks tiles of 48 consecutive frames.  The 7920 samples a tile
+// needs are staged into shared memory with ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) that
+// completes on an mbarrier; the copy of tile i+1 is issued before tile i is processed (double buffer), so HBM reads are
+// contiguous 31 KiB bursts and each sample is fetched from HBM once although frames overlap 2.5x.  A warp owns four
+// frames: each 16-lane half processes TWO frames at once, packed in the two halves of f32x2 registers, so every fp32
+// operation of the pipeline is a packed FADD2 / FMUL2 / FFMA2 (the fp32 peak of sm_100 is only reachable through the
+// packed forms, and at ~14 flop/B this kernel sits at the fp32 ridge, not the HBM one).  DC removal, pre-emphasis and
+// the window are applied in registers; the 512-point real FFT is a 256-point complex FFT (two in-lane DFT-16 passes
+// around one padded shared-memory transpose); then the real-FFT split, the power spectrum, the mel bank in segment
+// form (255 taps per frame instead of the reference's dense 257x128 matmul), log, and the optional (x-mean)/(2 std).
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -18,36 +21,40 @@
 #include "zk_internal.cuh"
 
 struct zk_fbank_plan {
-  float* d_win;       // [400]
-  float* d_tw;        // [16 lanes][16] complex: W256^(n2*k1)
-  float* d_w512;      // [128] complex
-  int* d_mel_start;   // [128]
-  float* d_mel_w;     // [MELW][128]
-  int* d_group_len;   // [8]
-  float preemph, log_floor;
+  float2* d_win2;      // [400] window, each value duplicated for the two packed frames
+  float4* d_tw;        // [16 k1][16 lanes] W256^(n2 k1) as (re, re, im, im)
+  float4* d_w512;      // [8 j][16 lanes]   W512^(L + 16 j) as (re, re, im, im)
+  float4* d_segw;      // [taps][16 lanes]  (lo, lo, hi, hi) mel weights x 1/4
+  int* d_seg_start;    // [128]
+  int glen[zk::fb::SEG_GROUPS], goff[zk::fb::SEG_GROUPS + 1];
+  float preemph, log_floor, log_of_floor;
   int device;
 };
 
 namespace zk {
 namespace fbk {
 using namespace fb;
+typedef cpxv<float2> cpx2;
+static_assert(sizeof(cpx2) == 16, "packed complex pair is one 16-byte shared-memory element");
 
-constexpr int TILE_FRAMES = 32, WARPS = 8, THREADS = WARPS * 32;
-constexpr int TILE_SAMPLES = (TILE_FRAMES - 1) * SHIFT + FRAME;  // 5360
-constexpr int SCRATCH = ZBUF + PBUF;                             // floats per half-warp
+constexpr int WARPS = 12, THREADS = WARPS * 32, TILE_FRAMES = 4 * WARPS;
+constexpr int TILE_SAMPLES = (TILE_FRAMES - 1) * SHIFT + FRAME;  // 7920
+constexpr int UNIT_SCRATCH = 16 * TPITCH * 4;                    // floats per 16-lane half: the transpose buffer
+static_assert(UNIT_SCRATCH >= 2 * 512, "exchange + power buffers alias the transpose buffer");
 // shared memory carve-up (floats)
-constexpr int OFF_SAMPLES = 0;
-constexpr int OFF_WIN = OFF_SAMPLES + 2 * TILE_SAMPLES;
-constexpr int OFF_W512 = OFF_WIN + FRAME;
-constexpr int OFF_MELW = OFF_W512 + 256;
-constexpr int OFF_MELSTART = OFF_MELW + MELW * NMEL;
-constexpr int OFF_GROUP = OFF_MELSTART + NMEL;
-constexpr int OFF_SCRATCH = OFF_GROUP + 8;
-constexpr int OFF_BAR = OFF_SCRATCH + 2 * WARPS * SCRATCH;
+constexpr int OFF_SAMPLES = 0;                               // [2][TILE_SAMPLES] landing buffers of the bulk copies
+constexpr int OFF_WIN = OFF_SAMPLES + 2 * TILE_SAMPLES;      // window taps, each duplicated (f32x2)
+constexpr int OFF_TW = OFF_WIN + 2 * FRAME;
+constexpr int OFF_W512 = OFF_TW + 16 * 16 * 4;
+constexpr int OFF_SEGW = OFF_W512 + 8 * 16 * 4;
+constexpr int OFF_SEGSTART = OFF_SEGW + SEG_TAPS_MAX * 16 * 4;
+constexpr int OFF_SCRATCH = OFF_SEGSTART + NMEL;
+constexpr int OFF_BAR = OFF_SCRATCH + 2 * WARPS * UNIT_SCRATCH;
 constexpr int SMEM_BYTES = (OFF_BAR + 4) * 4;
-static_assert((OFF_SCRATCH % 2) == 0 && (SCRATCH % 2) == 0 && (ZBUF % 2) == 0, "float2 alignment");
-static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
-static_assert(SMEM_BYTES <= 113 * 1024, "two CTAs per SM");
+static_assert(OFF_WIN % 4 == 0 && OFF_TW % 4 == 0 && OFF_W512 % 4 == 0 && OFF_SEGW % 4 == 0 && OFF_SCRATCH % 4 == 0 &&
+                  UNIT_SCRATCH % 4 == 0 && OFF_BAR % 2 == 0,
+              "16-byte alignment of the vector tables");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Job {
   const float* wave;     // segment s starts at wave + s*src_pitch
@@ -60,31 +67,52 @@ struct Job {
   float mean, std2;
 };
 
+// Scalar shared-memory load that the compiler cannot fuse with its neighbours: nvcc 12.9 turns the loads of
+// x[m - 1], x[m], x[m + 1] (pre-emphasis neighbour and the sample pair) into LDS.64 / LDS.128 although m - 1 is odd,
+// which faults with "misaligned address".
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+struct PairLoad {  // samples of two frames of the staged tile, packed; pair index i = samples 2 i, 2 i + 1
+  uint32_t a;      // shared address of the first frame
+  uint32_t db;     // byte offset of the second frame relative to the first (0 when it is a clamped duplicate)
+  __device__ __forceinline__ float2 even(int i) const { return make_float2(lds_f32(a + 8 * i), lds_f32(a + 8 * i + db)); }
+  __device__ __forceinline__ float2 odd(int i) const {
+    return make_float2(lds_f32(a + 8 * i + 4), lds_f32(a + 8 * i + 4 + db));
+  }
+};
+struct WindowLoad {  // window taps, each duplicated for the two packed frames
+  const float2* w;
+  __device__ __forceinline__ float2 even(int i) const { return w[2 * i]; }
+  __device__ __forceinline__ float2 odd(int i) const { return w[2 * i + 1]; }
+};
+
 template <bool BULK>
-__global__ void __launch_bounds__(THREADS, 2) fbank_kernel(const zk_fbank_plan plan, const Job job) {
+__global__ void __launch_bounds__(THREADS, 1) fbank_kernel(const zk_fbank_plan plan, const Job job) {
   extern __shared__ __align__(16) float sm[];
   float* samples = sm + OFF_SAMPLES;
-  float* win = sm + OFF_WIN;
-  float* w512 = sm + OFF_W512;
-  float* mel_w = sm + OFF_MELW;
-  int* mel_start = reinterpret_cast<int*>(sm + OFF_MELSTART);
-  int* group_len = reinterpret_cast<int*>(sm + OFF_GROUP);
+  float2* win2 = reinterpret_cast<float2*>(sm + OFF_WIN);
+  cpx2* tw = reinterpret_cast<cpx2*>(sm + OFF_TW);
+  cpx2* w512 = reinterpret_cast<cpx2*>(sm + OFF_W512);
+  float4* segw = reinterpret_cast<float4*>(sm + OFF_SEGW);
+  int* seg_start = reinterpret_cast<int*>(sm + OFF_SEGSTART);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = lane & 15, half = lane >> 4;
-  float* tbuf = sm + OFF_SCRATCH + (warp * 2 + half) * SCRATCH;
-  float* pbuf = tbuf + ZBUF;
+  const int L = lane & 15, unit = lane >> 4;
+  float* scratch = sm + OFF_SCRATCH + (warp * 2 + unit) * UNIT_SCRATCH;
+  cpx2* tbuf = reinterpret_cast<cpx2*>(scratch);              // [16 k1][TPITCH]   transpose
+  cpx2* xbuf = reinterpret_cast<cpx2*>(scratch);              // [8][16]           upper half of Z for the partner lane
+  float2* pbuf = reinterpret_cast<float2*>(scratch + 512);    // [256]             power spectrum
+  float2* hbuf = reinterpret_cast<float2*>(scratch);          // [128]             rising-slope sums for the next filter
 
-  for (int i = tid; i < FRAME; i += THREADS) win[i] = plan.d_win[i];
-  for (int i = tid; i < 256; i += THREADS) w512[i] = plan.d_w512[i];
-  for (int i = tid; i < MELW * NMEL; i += THREADS) mel_w[i] = plan.d_mel_w[i];
-  for (int i = tid; i < NMEL; i += THREADS) mel_start[i] = plan.d_mel_start[i];
-  if (tid < 8) group_len[tid] = plan.d_group_len[tid];
-  for (int i = L; i < PBUF; i += 16) pbuf[i] = 0.f;
-  cpx tw[16];
-#pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) tw[k1] = {plan.d_tw[(L * 16 + k1) * 2], plan.d_tw[(L * 16 + k1) * 2 + 1]};
+  for (int i = tid; i < FRAME; i += THREADS) win2[i] = plan.d_win2[i];
+  for (int i = tid; i < 16 * 16; i += THREADS) reinterpret_cast<float4*>(tw)[i] = plan.d_tw[i];
+  for (int i = tid; i < 8 * 16; i += THREADS) reinterpret_cast<float4*>(w512)[i] = plan.d_w512[i];
+  for (int i = tid; i < SEG_TAPS_MAX * 16; i += THREADS) segw[i] = plan.d_segw[i];
+  for (int i = tid; i < NMEL; i += THREADS) seg_start[i] = plan.d_seg_start[i];
   if (BULK && tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -135,41 +163,90 @@ __global__ void __launch_bounds__(THREADS, 2) fbank_kernel(const zk_fbank_plan p
       __syncthreads();
     }
 
-#pragma unroll 1
-    for (int round = 0; round < TILE_FRAMES / (2 * WARPS); ++round) {
-      const int fi = round * 2 * WARPS + warp * 2 + half;
-      const bool live = fi < nf;
-      const float* xs = xs_tile + (live ? fi : nf - 1) * SHIFT;
-      float x[13][2];
-      float s = lane_load(xs, L, x);
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      const float mean = __fdiv_rn(s, (float)FRAME);
-      lane_stage1(xs, win, L, x, mean, plan.preemph, tw, tbuf);
-      __syncwarp();
-      cpx z[16];
-      lane_stage2(tbuf, L, z);
-      __syncwarp();
-      lane_store_z(z, L, tbuf);
-      __syncwarp();
-      lane_power(z, tbuf, w512, L, pbuf);
-      __syncwarp();
-      float o[8];
-      lane_mel(pbuf, mel_start, mel_w, group_len, L, plan.log_floor, o);
-      if (live) {
-        float* dst = job.out + (out_row + fi) * NMEL + L;
+    // this half-warp's two frames (clamped to the last frame of a partial tile; clamped frames are not stored)
+    const int fa = warp * 4 + unit * 2, fb = fa + 1;
+    const int ca = min(fa, nf - 1), cb = min(fb, nf - 1);
+    if (warp * 4 < nf) {  // warp-uniform: at least one live frame in this warp
+      PairLoad ld{smem_u32(xs_tile + ca * SHIFT), (uint32_t)((cb - ca) * SHIFT * 4)};
+      cpx2 z[16];
+      {
+        float2 x0[13], x1[13], xp[13];
+        float2 s = lane_load<float2>(ld, L, x0, x1, xp);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = o[i];
-          if (job.normalize) v = __fdiv_rn(__fsub_rn(v, job.mean), job.std2);
-          dst[16 * i] = v;
+        for (int o = 8; o > 0; o >>= 1) {
+          s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+          s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        }
+        const float2 mean = make_float2(__fdiv_rn(s.x, (float)FRAME), __fdiv_rn(s.y, (float)FRAME));
+        lane_stage1<float2>(x0, x1, xp, mean, plan.preemph, WindowLoad{win2}, L, tw + L, 16, z);
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) tbuf[k1 * TPITCH + L] = z[k1];
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) z[n2] = tbuf[L * TPITCH + n2];
+      dft16(z);  // z[k2] = Z[L + 16 k2]
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xbuf[i * 16 + L] = z[8 + i];
+      __syncwarp();
+      {
+        const int partner = (16 - L) & 15;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const cpx2 other = xbuf[(7 - j) * 16 + partner];      // Z[256 - k] for L != 0
+          const cpx2 own = z[(16 - j) & 15];                    // lane 0: Z[256 - 16 j] (j = 0: Z[0] itself)
+          const cpx2 b = (L == 0) ? own : other;
+          const cpx2 w = w512[j * 16 + L];
+          float2 pk, pnk;
+          split_power<float2>(z[j], b, w.re, w.im, pk, pnk);
+          pbuf[L + 16 * j] = pk;
+          if (L + 16 * j != 0) pbuf[NZ - L - 16 * j] = pnk;
+        }
+        if (L == 0) {
+          const float2 q = vfma(z[8].re, z[8].re, vmul(z[8].im, z[8].im));
+          pbuf[128] = make_float2(4.0f * q.x, 4.0f * q.y);
         }
       }
       __syncwarp();
+      float2 lo[SEG_GROUPS], hi[SEG_GROUPS];
+#pragma unroll
+      for (int i = 0; i < SEG_GROUPS; ++i) {
+        const int st = seg_start[L + 16 * i];
+        float2 al = make_float2(0.f, 0.f), ah = make_float2(0.f, 0.f);
+        const int g0 = plan.goff[i], gl = plan.glen[i];
+        for (int t = 0; t < gl; ++t) {
+          const float2 p = pbuf[min(st + t, NZ - 1)];
+          const float4 w = segw[(g0 + t) * 16 + L];
+          al = vfma(p, make_float2(w.x, w.y), al);
+          ah = vfma(p, make_float2(w.z, w.w), ah);
+        }
+        lo[i] = al;
+        hi[i] = ah;
+      }
+      // xbuf (aliased by hbuf) was last read before the previous __syncwarp
+#pragma unroll
+      for (int i = 0; i < SEG_GROUPS; ++i) hbuf[L + 16 * i] = hi[i];
+      __syncwarp();
+      float* dst_a = job.out + (out_row + fa) * NMEL + L;
+      float* dst_b = job.out + (out_row + fb) * NMEL + L;
+      const bool live_a = fa < nf, live_b = fb < nf;
+#pragma unroll
+      for (int i = 0; i < SEG_GROUPS; ++i) {
+        const int r = L + 16 * i;
+        float2 e = lo[i];
+        if (r > 0) e = vadd(e, hbuf[r - 1]);
+        float va = e.x > plan.log_floor ? __logf(e.x) : plan.log_of_floor;
+        float vb = e.y > plan.log_floor ? __logf(e.y) : plan.log_of_floor;
+        if (job.normalize) {
+          va = __fdiv_rn(__fsub_rn(va, job.mean), job.std2);
+          vb = __fdiv_rn(__fsub_rn(vb, job.mean), job.std2);
+        }
+        if (live_a) dst_a[16 * i] = va;
+        if (live_b) dst_b[16 * i] = vb;
+      }
     }
-    __syncthreads();  // every warp is done with xs_tile before it is refilled
+    __syncthreads();  // every warp is done with xs_tile (and its scratch) before the tile buffer is refilled
   }
 }
 
@@ -192,7 +269,7 @@ static int launch_fbank(const zk_fbank_plan* plan, Job job, cudaStream_t stream)
   }
   if (job.num_tiles <= 0) return 0;
   const bool bulk = (reinterpret_cast<uintptr_t>(job.wave) % 16 == 0) && (job.src_pitch % 4 == 0);
-  long long grid = job.num_tiles < 2LL * num_sms() ? job.num_tiles : 2LL * num_sms();
+  long long grid = job.num_tiles < (long long)num_sms() ? job.num_tiles : (long long)num_sms();
   ProfScope prof(ZK_K_FBANK, stream);
   if (bulk)
     fbank_kernel<true><<<(int)grid, THREADS, SMEM_BYTES, stream>>>(*plan, job);
@@ -423,26 +500,51 @@ int zk_fbank_plan_create(const float* h_window, const float* h_mel, int num_mel,
   const int bad = build_host_tables(h_mel, *t);
   if (bad) {
     delete t;
-    zk::set_error("zk_fbank_plan_create: mel filter %d spans more than %d FFT bins", bad - 1, MELW);
+    zk::set_error("zk_fbank_plan_create: the mel bank is not triangular (FFT bin %d does not feed two adjacent filters)",
+                  bad - 1);
     return ZK_ERR_SHAPE;
   }
   zk_fbank_plan* p = new zk_fbank_plan();
   memset(p, 0, sizeof(*p));
   p->preemph = preemph;
   p->log_floor = log_floor;
+  p->log_of_floor = logf(log_floor);
+  for (int i = 0; i < SEG_GROUPS; ++i) p->glen[i] = t->glen[i];
+  for (int i = 0; i <= SEG_GROUPS; ++i) p->goff[i] = t->goff[i];
   cudaGetDevice(&p->device);
+  // device layouts: every value duplicated for the two frames packed in f32x2
+  float* win2 = new float[2 * FRAME];
+  for (int i = 0; i < FRAME; ++i) win2[2 * i] = win2[2 * i + 1] = h_window[i];
+  float* tw4 = new float[16 * 16 * 4];
+  for (int i = 0; i < 16 * 16; ++i) {
+    tw4[4 * i] = tw4[4 * i + 1] = t->tw[2 * i];
+    tw4[4 * i + 2] = tw4[4 * i + 3] = t->tw[2 * i + 1];
+  }
+  float* w4 = new float[8 * 16 * 4];
+  for (int i = 0; i < 8 * 16; ++i) {
+    w4[4 * i] = w4[4 * i + 1] = t->w512[2 * i];
+    w4[4 * i + 2] = w4[4 * i + 3] = t->w512[2 * i + 1];
+  }
+  float* s4 = new float[SEG_TAPS_MAX * 16 * 4];
+  for (int i = 0; i < SEG_TAPS_MAX * 16; ++i) {
+    s4[4 * i] = s4[4 * i + 1] = t->seg_w[2 * i];
+    s4[4 * i + 2] = s4[4 * i + 3] = t->seg_w[2 * i + 1];
+  }
   cudaError_t e = cudaSuccess;
   auto up = [&](void** dst, const void* src, size_t bytes) {
     if (e != cudaSuccess) return;
     e = cudaMalloc(dst, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
   };
-  up((void**)&p->d_win, h_window, FRAME * 4);
-  up((void**)&p->d_tw, t->tw, sizeof(t->tw));
-  up((void**)&p->d_w512, t->w512, sizeof(t->w512));
-  up((void**)&p->d_mel_start, t->start, sizeof(t->start));
-  up((void**)&p->d_mel_w, t->melw, sizeof(t->melw));
-  up((void**)&p->d_group_len, t->glen, sizeof(t->glen));
+  up((void**)&p->d_win2, win2, 2 * FRAME * 4);
+  up((void**)&p->d_tw, tw4, 16 * 16 * 16);
+  up((void**)&p->d_w512, w4, 8 * 16 * 16);
+  up((void**)&p->d_segw, s4, SEG_TAPS_MAX * 16 * 16);
+  up((void**)&p->d_seg_start, t->seg_start, sizeof(t->seg_start));
+  delete[] win2;
+  delete[] tw4;
+  delete[] w4;
+  delete[] s4;
   delete t;
   if (e != cudaSuccess) {
     zk_fbank_plan_destroy(p);
@@ -454,12 +556,11 @@ int zk_fbank_plan_create(const float* h_window, const float* h_mel, int num_mel,
 
 void zk_fbank_plan_destroy(zk_fbank_plan* p) {
   if (!p) return;
-  cudaFree(p->d_win);
+  cudaFree(p->d_win2);
   cudaFree(p->d_tw);
   cudaFree(p->d_w512);
-  cudaFree(p->d_mel_start);
-  cudaFree(p->d_mel_w);
-  cudaFree(p->d_group_len);
+  cudaFree(p->d_segw);
+  cudaFree(p->d_seg_start);
   delete p;
 }
 
