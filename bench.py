@@ -40,6 +40,16 @@ TOKENS, HID, MLP = 1214, 768, 3072
 METRIC, UNIT = "two_stage_windows_per_s", "windows/s"
 
 
+def load_traffic():
+    """DRAM bytes per full-batch fc1 launch from the committed ncu capture (profiles/roofline_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p))["gemm_fc1"]
+        return int(d["dram_bytes_read"] + d["dram_bytes_write"]), d["rows"]
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,6 +280,7 @@ def run_ours(args):
     flops_per_launch = 2.0 * (windows_fwd * TOKENS) * HID * MLP * full_fc1 / max(1, fc1_n)
     achieved = flops_per_launch / (fc1_ms / max(1, fc1_n) * 1e-3) / 1e12 if fc1_ms > 0 else None
     peak = peaks["bf16_sustained"]
+    traffic, traffic_rows = load_traffic()
     gemm_ms = sum(prof[c][0] for c in ("gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2", "gemm_patch"))
     breakdown = {c: round(v[0] / args.steps, 3) for c, v in prof.items() if v[1]}
     model_tflops = (n + k) / max(1, world) * GFLOP_PER_WINDOW / 1e3 / (ms / 1000.0)
@@ -291,7 +302,9 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BIAS_GELU> (fc1, M=batch*1214, N=3072, K=768)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                     "traffic": traffic, "traffic_note": (f"dram read+write of one {traffic_rows}-row launch, ncu --set full "
+                                                          "(profiles/roofline_traffic.json)") if traffic else None,
+                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                      "flops_per_launch": flops_per_launch, "launches": fc1_n},
         "kernel_ms_per_step": breakdown,
         "model_tflops_dense_equivalent": model_tflops, "model_tflops_executed": model_tflops_exec,

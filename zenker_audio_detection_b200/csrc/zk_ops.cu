@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
   extern __shared__ float ah_sm[];  // scores [2][tokens], then q [2][64], reduction scratch
   float* sc = ah_sm;
   float* qs = ah_sm + 2 * tokens;
-  float* red = qs + 2 * AH_D;       // [2][8] warp partials, later [2][2][64] partial outputs
+  float* red = qs + 2 * AH_D;       // [2][8] warp partials, later [8][2][64] partial outputs
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
   if (tid < 2 * AH_D)
@@ -206,21 +206,51 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
     l1 += red[8 + i];
   }
   __syncthreads();
-  // o[qi][d] = sum_key p[qi][key] V[key][d]: thread = (key half, query, dim); a warp reads 64-byte runs of V rows
-  const int d = tid & 63, qi = (tid >> 6) & 1, half = tid >> 7;
-  const float* pr = sc + qi * tokens;
-  float acc = 0.f;
-  for (int key = half; key < tokens; key += 2) acc = fmaf(pr[key], __bfloat162float(vbase[(long long)key * AH_QKV + d]), acc);
-  red[(half * 2 + qi) * AH_D + d] = acc;
+  // o[qi][d] = sum_key p[qi][key] V[key][d]: warp w takes keys w, w + 8, ...; lane l owns dims 2 l, 2 l + 1, so one
+  // warp instruction reads one whole 128-byte V row; four keys in flight per iteration, partials reduced over the warps
+  const __nv_bfloat16* vrow = vbase + 2 * lane;
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+  int key = warp;
+  for (; key + 24 < tokens; key += 32) {
+    uint32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint32_t*>(vrow + (long long)(key + 8 * u) * AH_QKV));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float lo = __uint_as_float(v[u] << 16), hi = __uint_as_float(v[u] & 0xffff0000u);
+      const float p0 = sc[key + 8 * u], p1 = sc[tokens + key + 8 * u];
+      a00 = fmaf(p0, lo, a00);
+      a01 = fmaf(p0, hi, a01);
+      a10 = fmaf(p1, lo, a10);
+      a11 = fmaf(p1, hi, a11);
+    }
+  }
+  for (; key < tokens; key += 8) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(vrow + (long long)key * AH_QKV));
+    const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+    const float p0 = sc[key], p1 = sc[tokens + key];
+    a00 = fmaf(p0, lo, a00);
+    a01 = fmaf(p0, hi, a01);
+    a10 = fmaf(p1, lo, a10);
+    a11 = fmaf(p1, hi, a11);
+  }
+  float* part = red;  // [8 warps][2 queries][64 dims]
+  part[(warp * 2 + 0) * AH_D + 2 * lane] = a00;
+  part[(warp * 2 + 0) * AH_D + 2 * lane + 1] = a01;
+  part[(warp * 2 + 1) * AH_D + 2 * lane] = a10;
+  part[(warp * 2 + 1) * AH_D + 2 * lane + 1] = a11;
   __syncthreads();
   if (tid < 2 * AH_D) {
-    const float o = (red[qi * AH_D + d] + red[(2 + qi) * AH_D + d]) / (qi ? l1 : l0);
-    out2[(long long)(2 * b + qi) * LN_COLS + h * AH_D + d] = __float2bfloat16(o);
+    const int d = tid & 63, qi = tid >> 6;
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += part[(w * 2 + qi) * AH_D + d];
+    out2[(long long)(2 * b + qi) * LN_COLS + h * AH_D + d] = __float2bfloat16(o / (qi ? l1 : l0));
   }
 }
 
 int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, int tokens, cudaStream_t stream) {
-  const size_t smem = (size_t)(2 * tokens + 2 * AH_D + 4 * AH_D) * sizeof(float);
+  const size_t smem = (size_t)(2 * tokens + 2 * AH_D + 16 * AH_D) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("attention_head_rows: %d tokens do not fit the score buffer", tokens);
     return ZK_ERR_SHAPE;
