@@ -31,3 +31,20 @@ def test_attention(B, T, scale):
     assert err <= 3.5e-2, err  # (one bf16 ulp at |o| in [4, 8) is 3.1e-2)
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel <= 1e-2, rel
+
+
+@pytest.mark.parametrize("seed", [3, 19])
+def test_attention_does_not_depend_on_the_neighbouring_window(seed):
+    """The rows past the last token of a window (1214 = 9 * 128 + 62) belong to the NEXT window of the batch: they are
+    masked as keys and never stored as queries, and they must not influence the window's own rows in any other way
+    (seed 19 used to: an out-of-window row sharing a warp with real ones triggered the warp-wide max update)."""
+    from zenker_audio_detection_b200 import ops
+
+    T = 1214
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    qkv = torch.randn(2 * T, 2304, device="cuda", generator=g)
+    qkv[:, :1536] *= 2.5
+    qkv = qkv.to(torch.bfloat16)
+    both = ops.attention(qkv, 2, T)
+    alone = ops.attention(qkv[:T].contiguous(), 1, T)
+    assert torch.equal(both[:T], alone)

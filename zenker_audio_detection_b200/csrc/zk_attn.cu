@@ -119,7 +119,7 @@ struct SoftmaxState {
 // keeps a warp's MUFU demand uniform over the block instead of 0 % during a max phase and 100 % after it, which is
 // what lets the two softmax warps of a scheduler share the MUFU pipe without phase locking.
 template <bool RAGGED, bool FIRST, int POLY>
-__device__ __forceinline__ void softmax_block(uint32_t n, int kmax, uint32_t t_s, uint32_t t_o, uint32_t t_p,
+__device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_valid, uint32_t t_s, uint32_t t_o, uint32_t t_p,
                                               uint64_t* s_free, uint64_t* pv_done, SoftmaxState& st, long long* trj) {
   uint32_t s[128];
   tmem_ld32_at<0>(t_s, s);
@@ -191,9 +191,13 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, uint32_t t_s
     }
     if (FIRST || pass == 1) break;
     const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    if (!__any_sync(0xffffffffu, (mx - st.m) * SCALE_LOG2E > RESCALE_TAU)) break;
+    // Only rows that are real queries of this window vote, and only rows that exceed the threshold themselves move
+    // their maximum: a row's result must not depend on what else shares its warp (the rows past the last token of a
+    // window hold the NEXT window's queries, i.e. they change with the batch composition).
+    const bool exceed = row_valid && (mx - st.m) * SCALE_LOG2E > RESCALE_TAU;
+    if (!__any_sync(0xffffffffu, exceed)) break;
     // rare: advance the running maximum, rescale the accumulator in TMEM (whole warp, tcgen05 is collective), redo
-    const float mn = fmaxf(st.m, mx);
+    const float mn = exceed ? mx : st.m;
     const float alpha = fast_exp2((st.m - mn) * SCALE_LOG2E);
     st.m = mn;
     st.l2a.x *= alpha; st.l2a.y *= alpha; st.l2b.x *= alpha; st.l2b.y *= alpha;
@@ -374,6 +378,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     for (int it = 0; it < my_items; ++it) {
       int b, h, qb;
       item_coords(it, b, h, qb);
+      const bool row_valid = (qb * QTILES + t) * BQ + row < tokens;
       for (int j = 0; j < nkv; ++j, ++n) {
         long long* trj = (tracer && n < 15) ? tr + 8 + n * 8 : nullptr;
         if (trj) trj[0] = clock64();
@@ -383,14 +388,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
         if (kmax < BKV) {
           if (j == 0)
-            softmax_block<true, true, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, true, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
-            softmax_block<true, false, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, false, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         } else {
           if (j == 0)
-            softmax_block<false, true, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, true, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
-            softmax_block<false, false, POLY>(n, kmax, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, false, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         }
         tc_fence_before();
         mbar_arrive(&p_full[t]);
