@@ -1,0 +1,127 @@
+"""Ingest + orchestration around the hot path: the WAV reader that replaces torchaudio.load /
+torchaudio.info (TorchCodec is absent in this image) and the in-process batch runner that replaces
+run_batch_simple_2stage.py.  CPU-only checks here; the end-to-end run is in test_gpu_pipeline.py."""
+import io
+import json
+import os
+import struct
+import wave
+
+import numpy as np
+import pytest
+
+from zenker_audio_detection_b200 import batch, wavio
+
+
+def _tone(n, ch, seed):
+    r = np.random.default_rng(seed)
+    return (r.standard_normal((ch, n)) * 0.2).clip(-1, 1).astype(np.float32)
+
+
+def test_wav_pcm16_matches_the_stdlib_reader(tmp_path):
+    x = _tone(4801, 2, 1)
+    p = str(tmp_path / "a.wav")
+    wavio.write_pcm16(p, x, 48000)
+    data, sr = wavio.read(p)
+    assert sr == 48000 and data.dtype == np.int16 and data.shape == (4801, 2)
+    with wave.open(p, "rb") as w:
+        assert (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()) == (48000, 2, 2, 4801)
+        ref = np.frombuffer(w.readframes(4801), dtype="<i2").reshape(4801, 2)
+    assert np.array_equal(data, ref)
+    assert np.abs(data.T / 32768.0 - x).max() <= 0.5 / 32768 + 1e-7
+    wi = wavio.info(p)
+    assert (wi.sample_rate, wi.num_frames, wi.num_channels, wi.bits_per_sample, wi.encoding) == (48000, 4801, 2, 16, "PCM_S")
+
+
+@pytest.mark.parametrize("tag,bits,dtype,scale", [(1, 8, np.uint8, 128.0), (1, 24, None, 8388608.0), (1, 32, "<i4", 2147483648.0),
+                                                  (3, 32, "<f4", 1.0), (3, 64, "<f8", 1.0)])
+def test_wav_other_encodings_are_normalised_like_torchaudio(tmp_path, tag, bits, dtype, scale):
+    x = _tone(1000, 1, bits)[0]
+    if tag == 3:
+        raw = x.astype(dtype).tobytes()
+        want = x.astype(dtype).astype(np.float32)
+    elif bits == 8:
+        q = np.clip(np.round(x * 128.0) + 128, 0, 255).astype(np.uint8)
+        raw, want = q.tobytes(), (q.astype(np.float32) - 128.0) / 128.0
+    elif bits == 24:
+        q = np.clip(np.round(x * scale), -scale, scale - 1).astype(np.int32)
+        raw = b"".join(struct.pack("<i", int(v))[:3] for v in q)
+        want = q.astype(np.float32) / np.float32(scale)
+    else:
+        q = np.clip(np.round(x.astype(np.float64) * scale), -scale, scale - 1).astype(np.int64).astype(dtype)
+        raw, want = q.tobytes(), q.astype(np.float32) / np.float32(scale)
+    p = tmp_path / "b.wav"
+    with open(p, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + 14 + len(raw)) + b"WAVE")
+        f.write(b"LIST" + struct.pack("<I", 5) + b"abcde" + b"\0")  # an odd-sized chunk before fmt: word alignment
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, tag, 1, 16000, 16000 * bits // 8, bits // 8, bits))
+        f.write(b"data" + struct.pack("<I", len(raw)) + raw)
+    data, sr = wavio.read(str(p))
+    assert sr == 16000 and data.dtype == np.float32 and data.shape == (1, 1000)
+    assert np.array_equal(data[0], want)
+
+
+def test_wav_rejects_garbage(tmp_path):
+    p = tmp_path / "c.wav"
+    p.write_bytes(b"RIFF\x00\x00\x00\x00WAVEfmt ")
+    with pytest.raises(wavio.WavError):
+        wavio.read(str(p))
+    p.write_bytes(b"not a wav file at all")
+    with pytest.raises(wavio.WavError):
+        wavio.info(str(p))
+
+
+def _tree(tmp_path):
+    root = tmp_path / "long"
+    lens = {"Healthy/224": [1600, 800, 2400], "Zenker/301": [1200, 900], "Zenker/17": [500]}
+    for rel, ns in lens.items():
+        d = root / rel
+        d.mkdir(parents=True)
+        for i, n in enumerate(ns):
+            wavio.write_pcm16(str(d / f"rec{i}.wav"), _tone(n, 1, n), 16000)
+        (d / "notes.txt").write_text("x")
+    ids = tmp_path / "ids"
+    ids.mkdir()
+    (ids / "test_ids_fold3.txt").write_text("Healthy/224\n\nZenker/301\nZenker/17\n")
+    return root, ids
+
+
+def test_discover_two_files_follows_the_reference(tmp_path):
+    root, _ = _tree(tmp_path)
+    two = batch.discover_two_files(str(root), "301", "*.wav")
+    assert [os.path.basename(p) for p in two] == ["rec0.wav", "rec1.wav"]  # sorted (ref:128)
+    longest = batch.discover_two_files(str(root), "224", "*.wav")  # > 2 files: the two with most frames (ref:129-137)
+    assert [os.path.basename(p) for p in longest] == ["rec2.wav", "rec0.wav"]
+    with pytest.raises(ValueError, match="Expected exactly 2 files for patient 17, found 1"):
+        batch.discover_two_files(str(root), "17", "*.wav")
+
+
+def test_ids_thresholds_and_plan(tmp_path, capsys):
+    root, ids = _tree(tmp_path)
+    assert batch.read_ids(str(ids / "test_ids_fold3.txt")) == ["224", "301", "17"]
+    cfg = {"folds": {"3": {"stage1": {"threshold": 0.61}, "stage2": {"threshold": 0.35}}},
+           "thresholds": {"stage1": {"threshold": 0.9}}}
+    assert batch.resolve_thresholds(cfg, 3) == (0.61, 0.35)       # per-fold block wins (ref batch:97-108)
+    assert batch.resolve_thresholds({"thresholds": {"stage2": {"threshold": 0.4}}}, 3) == (None, 0.4)
+    assert batch.resolve_thresholds(None, 3) == (None, None)
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "301_2stage.json").write_text("{}")
+    args = batch.build_arg_parser().parse_args(["--fold", "3", "--ids-root", str(ids), "--long-audio-root", str(root),
+                                                "--output-dir", str(out), "--dry-run"])
+    plans = [batch.plan_patients(args, r, 2)[0] for r in range(2)]
+    assert sorted(pid for pl in plans for pid, _ in pl) == ["224"]  # 301 exists -> skipped, 17 has one file -> error
+    assert batch.run(args, 0, 1) == 0
+    printed = capsys.readouterr().out
+    assert "[SKIP] 301" in printed and "[ERROR] patient 17" in printed and "[RUN] rank 0: 224" in printed
+    args.force = True
+    assert sorted(pid for pid, _ in batch.plan_patients(args, 0, 1)[0]) == ["224", "301"]
+
+
+def test_batch_flags_are_the_launchers():
+    """ref batch:145-211 (+ the per-patient thresholds / batch size of refc:303-376 it forwards)."""
+    flags = {a.option_strings[0] for a in batch.build_arg_parser()._actions if a.option_strings}
+    for f in ("--fold", "--ids-root", "--long-audio-root", "--pattern", "--window-sec", "--hop-sec", "--plot",
+              "--output-dir", "--threshold-config", "--stage1-model-root", "--stage2-model-root",
+              "--stage1-forward-min-prob", "--stage2-argmax", "--extra", "--force", "--dry-run"):
+        assert f in flags, f

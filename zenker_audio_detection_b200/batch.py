@@ -1,0 +1,203 @@
+"""In-process replacement of ``src/run_batch_simple_2stage.py`` + ``src/test_long_audio_windows_2stage_cache.py``:
+
+    python -m zenker_audio_detection_b200.batch --fold 1 --long-audio-root data/long --output-dir outputs
+    torchrun --nproc-per-node 8 -m zenker_audio_detection_b200.batch ...        # patients sharded over the GPUs
+
+The reference launcher spawns one Python process per patient (ref batch:282-284), each of which reloads both models
+from disk; here both models are loaded once per rank, every rank takes its share of the fold's patients (longest
+first, ``dist.shard_recordings``), and each patient's ``<pid>_2stage.json`` is written in the schema of the script the
+launcher runs (refc:570-601), so ``utils/aggregate_2stage_results.py`` consumes the output directory unchanged.  The
+flags are the launcher's own (ref batch:145-211); ``--plot`` / ``--extra`` are accepted and ignored.  Patients are
+independent, so there is no collective at all on this path.
+"""
+from __future__ import annotations
+
+import argparse
+import fnmatch
+import json
+import os
+import sys
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from . import wavio
+
+
+def read_ids(ids_path: str) -> List[str]:
+    """ref batch:48-57: one ``Class/ID`` per line, the leaf is the patient id."""
+    patients = []
+    with open(ids_path, "r") as f:
+        for line in f:
+            line = line.strip()
+            if line:
+                patients.append(line.split("/")[-1])
+    return patients
+
+
+def resolve_thresholds(config: Optional[dict], fold: int) -> Tuple[Optional[float], Optional[float]]:
+    """ref batch:97-118: per-fold thresholds (``folds[str(fold)]``) win over the single ``thresholds`` block."""
+    if not config:
+        return None, None
+    block = config.get("folds", {}).get(str(fold)) if config.get("folds") else None
+    if block is None:
+        block = config.get("thresholds", {})
+    s1 = block.get("stage1", {}).get("threshold") if "stage1" in block else None
+    s2 = block.get("stage2", {}).get("threshold") if "stage2" in block else None
+    return s1, s2
+
+
+def discover_two_files(root: str, patient_id: str, pattern: str) -> List[str]:
+    """ref:119-142: every file matching ``pattern`` below a directory whose path contains the patient id, sorted; with
+    more than two, the two with the most frames (header only); anything but two is an error."""
+    base = os.path.abspath(root)
+    matches = []
+    for dirpath, _, filenames in os.walk(base):
+        if patient_id not in dirpath:
+            continue
+        for fn in filenames:
+            if fnmatch.fnmatch(fn, pattern):
+                matches.append(os.path.join(dirpath, fn))
+    matches = sorted(matches)
+    if len(matches) > 2:
+        lengths = []
+        for p in matches:
+            try:
+                lengths.append((p, wavio.info(p).num_frames))
+            except Exception:  # noqa: BLE001 - like the reference: unreadable files sort last
+                lengths.append((p, 0))
+        matches = [p for p, _ in sorted(lengths, key=lambda x: x[1], reverse=True)[:2]]
+    if len(matches) != 2:
+        raise ValueError(f"Expected exactly 2 files for patient {patient_id}, found {len(matches)}: {matches}")
+    return matches
+
+
+def default_model_root(stage: int, fold: int) -> str:
+    """refc:397-405 resolves ``<project_root>/runs/ast_classifier_stage<k>/fold<F>/best``; the project root here is the
+    working directory (this package does not live inside the reference checkout)."""
+    return os.path.join(os.getcwd(), "runs", f"ast_classifier_stage{stage}", f"fold{fold}", "best")
+
+
+def build_arg_parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(description="Two-stage window inference over every patient of a fold (B200, in process).")
+    ap.add_argument("--fold", type=int, required=True)
+    ap.add_argument("--ids-root", default=None, help="Directory containing test_ids_fold<fold>.txt (default: ./data_ast_stage2)")
+    ap.add_argument("--long-audio-root", required=True)
+    ap.add_argument("--pattern", default="*.wav")
+    ap.add_argument("--window-sec", type=float, default=1.0)
+    ap.add_argument("--hop-sec", type=float, default=0.5)
+    ap.add_argument("--batch-size", type=int, default=128)
+    ap.add_argument("--plot", action="store_true", help="accepted for compatibility; ignored")
+    ap.add_argument("--output-dir")
+    ap.add_argument("--threshold-config")
+    ap.add_argument("--stage1-model-root")
+    ap.add_argument("--stage2-model-root")
+    ap.add_argument("--stage1-threshold", type=float, default=0.5)
+    ap.add_argument("--stage2-threshold", type=float, default=0.5)
+    ap.add_argument("--stage1-forward-min-prob", type=float)
+    ap.add_argument("--stage2-argmax", action="store_true")
+    ap.add_argument("--extra", help="accepted for compatibility; ignored")
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--dry-run", action="store_true")
+    return ap
+
+
+def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str]]], List[str]]:
+    """-> (this rank's ``[(patient, [file_a, file_b])]``, log lines).  Every rank computes the same global plan."""
+    ids_root = args.ids_root or os.path.join(os.getcwd(), "data_ast_stage2")
+    ids_path = os.path.join(ids_root, f"test_ids_fold{args.fold}.txt")
+    if not os.path.exists(ids_path):
+        raise FileNotFoundError(f"IDs file not found: {ids_path}")
+    out_dir = args.output_dir or "outputs"
+    log, todo = [], []
+    for pid in read_ids(ids_path):
+        expected = os.path.join(out_dir, f"{pid}_2stage.json")
+        if os.path.exists(expected) and not args.force:
+            log.append(f"[SKIP] {pid} (exists: {expected})")  # ref batch:274-277
+            continue
+        try:
+            files = discover_two_files(args.long_audio_root, pid, args.pattern)
+        except ValueError as e:
+            log.append(f"[ERROR] patient {pid}: {e}")  # ref batch:286-289: a failing patient does not stop the batch
+            continue
+        todo.append((pid, files))
+    from .dist import shard_recordings
+
+    sizes = [sum(os.path.getsize(p) for p in files) for _, files in todo]
+    mine = shard_recordings(sizes, world)[rank] if todo else []
+    return [todo[i] for i in mine], log
+
+
+def run(args, rank: int = 0, world: int = 1) -> int:
+    cfg = None
+    if args.threshold_config and os.path.exists(args.threshold_config):
+        with open(args.threshold_config, "r") as f:
+            cfg = json.load(f)
+    t1, t2 = resolve_thresholds(cfg, args.fold)
+    thr1 = args.stage1_threshold if t1 is None else float(t1)
+    thr2 = args.stage2_threshold if t2 is None else float(t2)
+    s1_root = args.stage1_model_root or default_model_root(1, args.fold)
+    s2_root = args.stage2_model_root or default_model_root(2, args.fold)
+    out_dir = args.output_dir or "outputs"
+    os.makedirs(out_dir, exist_ok=True)
+    mine, log = plan_patients(args, rank, world)
+    if rank == 0:
+        for line in log:
+            print(line)
+    for pid, files in mine:
+        print(f"[RUN] rank {rank}: {pid}  A: {files[0]}  B: {files[1]}")
+    if args.dry_run or not mine:
+        return 0
+
+    import torch
+    from transformers import ASTConfig
+
+    from . import results
+    from .fx import ZenkerASTFeatureExtractor
+    from .model import ZenkerASTForAudioClassification
+    from .pipeline import TwoStagePipeline
+
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+
+    def load(root: str, labels: Sequence[str]):  # ref:86-98
+        fx = ZenkerASTFeatureExtractor.from_pretrained(root)
+        cfg_ = ASTConfig.from_pretrained(root)
+        cfg_.label2id = {l: i for i, l in enumerate(labels)}
+        cfg_.id2label = {i: l for i, l in enumerate(labels)}
+        return fx, ZenkerASTForAudioClassification.from_pretrained(root, config=cfg_).to(device).eval()
+
+    fx1, m1 = load(s1_root, ["Idle", "Swallow"])
+    fx2, m2 = load(s2_root, ["Healthy", "Zenker"])
+    pipe = TwoStagePipeline(m1, fx1, m2, fx2, batch_size=args.batch_size, window_sec=args.window_sec, hop_sec=args.hop_sec,
+                            stage1_threshold=thr1, stage2_threshold=thr2,
+                            stage1_forward_min_prob=args.stage1_forward_min_prob, stage2_argmax=args.stage2_argmax,
+                            device=device)
+    failures = 0
+    for pid, files in mine:
+        try:
+            summaries = []
+            for path in files:
+                samples, sr = wavio.read(path)
+                summaries.append(pipe.run_waveform(samples, sr).summary)
+            doc = results.build_document(s1_root, s2_root, args.window_sec, args.hop_sec, args.batch_size, thr1, files,
+                                         summaries, variant="cached", stage2_threshold=thr2,
+                                         stage1_forward_min_prob=args.stage1_forward_min_prob,
+                                         stage2_argmax=args.stage2_argmax, feature_cache_dir=None, disable_cache=True)
+            results.write_json(doc, os.path.join(out_dir, f"{pid}_2stage.json"))
+            print(f"[DONE] {pid} OK")
+        except Exception as e:  # noqa: BLE001 - ref batch:286-289: log and continue with the next patient
+            failures += 1
+            print(f"[ERROR] patient {pid}: {type(e).__name__}: {e}")
+    print("Batch complete." if world == 1 else f"Batch complete (rank {rank}).")
+    return failures
+
+
+def main(argv: Optional[Sequence[str]] = None) -> None:
+    args = build_arg_parser().parse_args(argv)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    failures = run(args, rank, world)
+    if failures:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

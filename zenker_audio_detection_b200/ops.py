@@ -53,6 +53,8 @@ def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Ten
         if w.dim() == 1:
             w = w.unsqueeze(1)
         n, ch = w.shape
+        if orig == new:  # same rate: only the 2^-15 scaling and the channel mean remain (identity tap)
+            taps, width = torch.ones(1, 1, dtype=torch.float32, device=w.device), 0
         n_out = (n * new + orig - 1) // orig
         out = torch.empty(n_out, dtype=torch.float32, device=w.device)
         check(lib.zk_resample_pcm16(w.data_ptr(), n, ch, taps.data_ptr(), orig, new, width, out.data_ptr(), n_out,
