@@ -125,3 +125,26 @@ def test_batch_flags_are_the_launchers():
               "--output-dir", "--threshold-config", "--stage1-model-root", "--stage2-model-root",
               "--stage1-forward-min-prob", "--stage2-argmax", "--extra", "--force", "--dry-run"):
         assert f in flags, f
+
+
+def test_patched_torchaudio_load_and_info(tmp_path):
+    """compat.patch_torchaudio: ``load_audio`` (ref:53-59) and ``discover_two_files`` (ref:132) keep working without
+    TorchCodec: float32 (channels, frames) in [-1, 1), sample rate, ``info(...).num_frames``."""
+    import torch
+    import torchaudio
+
+    from zenker_audio_detection_b200 import compat
+
+    x = _tone(3000, 2, 5)
+    p = str(tmp_path / "d.wav")
+    wavio.write_pcm16(p, x, 44100)
+    compat.patch_torchaudio()
+    try:
+        wav, sr = torchaudio.load(p)
+        assert sr == 44100 and wav.dtype == torch.float32 and tuple(wav.shape) == (2, 3000)
+        assert float((wav - torch.from_numpy(x)).abs().max()) <= 0.5 / 32768 + 1e-7
+        assert torchaudio.info(p).num_frames == 3000
+        mono = wav.mean(dim=0, keepdim=True)  # ref:55-56
+        assert tuple(mono.shape) == (1, 3000)
+    finally:
+        compat.unpatch_torchaudio()

@@ -11,9 +11,10 @@ def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         raise SystemExit("usage: python -m zenker_audio_detection_b200.run <script.py> [script args...]")
-    from .compat import patch_transformers
+    from .compat import patch_torchaudio, patch_transformers
 
     patch_transformers()
+    patch_torchaudio()  # WAV decoding without TorchCodec (ref:54, ref:132)
     script = argv[0]
     sys.argv = argv
     sys.path.insert(0, os.path.dirname(os.path.abspath(script)))

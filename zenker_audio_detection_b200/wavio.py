@@ -90,10 +90,14 @@ def read(path: str) -> Tuple[Union[np.ndarray], int]:
     with open(path, "rb") as f:
         wi = _read_header(f)
         f.seek(wi.data_offset)
+        n, c = wi.num_frames, wi.num_channels
+        if wi.encoding == "PCM_S" and wi.bits_per_sample == 16:
+            pcm = np.empty((n, c), dtype="<i2")  # read straight into the (writable) array handed to the H2D copy
+            got = f.readinto(memoryview(pcm).cast("B"))
+            if got != wi.data_bytes:
+                raise WavError(f"{path}: short read ({got} of {wi.data_bytes} bytes)")
+            return pcm, wi.sample_rate
         raw = f.read(wi.data_bytes)
-    n, c = wi.num_frames, wi.num_channels
-    if wi.encoding == "PCM_S" and wi.bits_per_sample == 16:
-        return np.frombuffer(raw, dtype="<i2").reshape(n, c), wi.sample_rate
     if wi.encoding == "PCM_U":
         x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
     elif wi.encoding == "PCM_S" and wi.bits_per_sample == 24:
