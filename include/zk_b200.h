@@ -160,6 +160,10 @@ int zk_gate_compact(const float* d_logits, int n, float threshold, float min_pro
                     int32_t* d_index, int32_t* d_count, zk_stream_t stream);
 /* softmax only (Stage 2: ref:111) */
 int zk_softmax2(const float* d_logits, int n, float* d_probs, zk_stream_t stream);
+/* Dataset normalisation statistics (utils/compute_ast_normalization_stats.py:77-80): d_acc[0] += sum(x), d_acc[1] +=
+ * sum(x^2) over n floats, accumulated in float64 (the caller zeroes d_acc before the first batch; zero-padded feature
+ * rows simply add 0, so the continuous or the padded layout give the same sums). */
+int zk_sum_sumsq_f64(const float* d_x, int64_t n, double* d_acc, zk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks, exported so the parity tests can pin each kernel separately.

@@ -51,3 +51,24 @@ def test_softmax2():
     logits = torch.randn(777, 2, device="cuda") * 4
     p = ops.softmax2(logits)
     assert (p - torch.softmax(logits, dim=1)).abs().max().item() <= 2e-7
+
+
+@pytest.mark.parametrize("n", [1, 3, 1027, 98 * 128 * 64])
+def test_feature_stats_match_the_float64_reference(n):
+    """utils/compute_ast_normalization_stats.py:77-95: float64 sums over the zero-padded features, unbiased std."""
+    from zenker_audio_detection_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n, device="cuda", generator=g) * 3.5 - 4.2
+    st = ops.FeatureStats()
+    half = n // 2
+    padded = 2 * n + 5  # the values stand for a zero-padded tensor of this many elements
+    st.update(x[:half].contiguous() if half % 4 == 0 else x[:half].clone(), padded_elements=padded - (n - half))
+    st.update(x[half:].clone(), padded_elements=n - half)
+    flat = torch.cat([x.double().cpu(), torch.zeros(padded - n, dtype=torch.float64)])
+    mean = flat.sum().item() / padded
+    var = max((flat ** 2).sum().item() / padded - mean * mean, 0.0) * (padded / (padded - 1))
+    got = st.result()
+    assert got["count"] == padded
+    assert abs(got["mean"] - mean) <= 1e-12 * max(1.0, abs(mean)) + 1e-13
+    assert abs(got["std"] - var ** 0.5) <= 1e-10 * max(1.0, var ** 0.5)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "zk_gate_compact": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "zk_softmax2": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "zk_sum_sumsq_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zk_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p]),
     "zk_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int,

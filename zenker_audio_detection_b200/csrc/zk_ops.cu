@@ -420,6 +420,44 @@ int head_logits(const float* x, int batch, int tokens, const float* fln_w, const
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ feature statistics
+// sum and sum of squares in fp64 (utils/compute_ast_normalization_stats.py:77-80 casts every batch to float64 first):
+// HBM-bound, 4 B per element; per-thread fp64 partials over float4 loads, warp shuffle, one atomicAdd pair per block.
+__global__ void __launch_bounds__(256) sum_sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+  double s = 0.0, q = 0.0;
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const double v = x[(n4 << 2) + threadIdx.x];
+    s += v;
+    q += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  __shared__ double red[2][8];
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      s += red[0][i];
+      q += red[1][i];
+    }
+    atomicAdd(acc, s);
+    atomicAdd(acc + 1, q);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gate + compaction
 // ref:111 softmax over 2 classes; ref:312-320 pred = (argmax == 1) & (p1 >= thr) with numpy's first-max tie
 // rule (argmax == 1 iff p1 > p0); refc:471-478 optional extra gate p1 >= min_prob applied to the forwarded set.
@@ -515,6 +553,23 @@ int zk_gate_compact(const float* d_logits, int n, float threshold, float min_pro
   zk::gate_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_logits, n, threshold, min_prob, d_probs, d_pred,
                                                                d_index, d_count);
   ZK_LAUNCH_CHECK("gate_compact_kernel");
+  return 0;
+}
+
+int zk_sum_sumsq_f64(const float* d_x, int64_t n, double* d_acc, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (n < 0 || !d_acc || (n > 0 && !d_x) || (reinterpret_cast<uintptr_t>(d_x) & 15)) {
+    zk::set_error("zk_sum_sumsq_f64: bad arguments (d_x must be 16-byte aligned)");
+    return ZK_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8LL * zk::num_sms()) blocks = 8LL * zk::num_sms();
+  zk::ProfScope prof(ZK_K_MISC, (cudaStream_t)stream);
+  zk::sum_sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, d_acc);
+  ZK_LAUNCH_CHECK("sum_sumsq_kernel");
   return 0;
 }
 

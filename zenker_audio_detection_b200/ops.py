@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional, Tuple, Union
 
 import torch
 
@@ -169,6 +169,32 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int) -> torch.Tensor:
     out = torch.empty((batch * tokens, HID), dtype=torch.bfloat16, device=qkv.device)
     check(lib.zk_attention_bf16(qkv.data_ptr(), out.data_ptr(), batch, tokens, _lib.stream_ptr()), "zk_attention_bf16")
     return out
+
+
+class FeatureStats:
+    """Running mean / std of un-normalised features, as utils/compute_ast_normalization_stats.py:55-95 computes them
+    (float64 sums over every element of the zero-padded ``(B, max_length, 128)`` tensors; unbiased std)."""
+
+    def __init__(self, device: Optional[Union[str, torch.device]] = None):
+        self.acc = torch.zeros(2, dtype=torch.float64, device=device or torch.device("cuda", torch.cuda.current_device()))
+        self.count = 0
+
+    def update(self, feats: torch.Tensor, padded_elements: Optional[int] = None) -> None:
+        """``feats``: CUDA float32, any shape.  ``padded_elements``: element count of the padded tensor these values
+        stand for (zero padding adds nothing to the sums; e.g. a compact (98,128) window counts as 1024*128)."""
+        lib = _lib.load()
+        f = _cuda(feats, torch.float32, "FeatureStats.update").reshape(-1)
+        check(lib.zk_sum_sumsq_f64(f.data_ptr(), f.numel(), self.acc.data_ptr(), _lib.stream_ptr()), "zk_sum_sumsq_f64")
+        self.count += int(padded_elements if padded_elements is not None else f.numel())
+
+    def result(self) -> dict:
+        if self.count == 0:
+            return {"mean": 0.0, "std": 0.0, "count": 0}
+        s, q = (float(v) for v in self.acc.cpu())
+        mean = s / self.count
+        var = max(q / self.count - mean * mean, 0.0)
+        var = var * (self.count / (self.count - 1)) if self.count > 1 else 0.0
+        return {"mean": float(mean), "std": float(var ** 0.5), "count": self.count}
 
 
 def softmax2(logits: torch.Tensor) -> torch.Tensor:
