@@ -10,6 +10,8 @@
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
 // MMAs of tile t+1.  Replaces the cuBLAS calls behind nn.Linear on the reference path
 // (HF:modeling_audio_spectrogram_transformer.py:146-148,197,230,243) and the patch-embedding conv (:88-96).
+#include <stdlib.h>
+
 #include "zk_b200.h"
 #include "zk_common.cuh"
 #include "zk_internal.cuh"
@@ -75,6 +77,26 @@ __device__ __forceinline__ void patch_store(const Params& p, long long row, int 
   }
 }
 
+// The same GELU for two values at once on the packed fp32 pipe (FFMA2 / FMUL2): the polynomial, the exponent argument
+// and the final product are packed, only the two MUFU pairs (rcp, ex2) and the sign handling stay scalar.  With
+// q(x) = x/2 * poly(t) * exp(-x^2/2) odd in x:  gelu(x) = max(x, 0) - |x| * (poly(t) * exp(-x^2/2) / 2).
+// 9 instructions per element instead of 18, which is what keeps the fc1 epilogue under the MMA time of its tile.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.x), 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.y), 1.0f)));
+  // coefficients pre-multiplied by 1/2
+  float2 poly = ffma2(t, make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  poly = ffma2(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  poly = ffma2(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  poly = ffma2(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  poly = fmul2(poly, t);
+  const float k = -0.5f * 1.44269504088896340736f;
+  const float2 arg = fmul2(fmul2(x, x), make_float2(k, k));
+  const float2 h = fmul2(poly, make_float2(fast_exp2(arg.x), fast_exp2(arg.y)));
+  return make_float2(fmaf(-fabsf(x.x), h.x, fmaxf(x.x, 0.f)), fmaf(-fabsf(x.y), h.y, fmaxf(x.y, 0.f)));
+}
+
 // 32 accumulator columns (+bias, optional GELU) -> 16 packed bf16 pairs
 template <bool GELU>
 __device__ __forceinline__ void bias_act_pack(const uint32_t (&r)[32], const float* bias, uint32_t (&pk)[16]) {
@@ -82,16 +104,14 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&r)[32], const flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 b = __ldg(bias4 + i);
-    float v0 = __uint_as_float(r[i * 4 + 0]) + b.x, v1 = __uint_as_float(r[i * 4 + 1]) + b.y;
-    float v2 = __uint_as_float(r[i * 4 + 2]) + b.z, v3 = __uint_as_float(r[i * 4 + 3]) + b.w;
+    float2 v01 = fadd2(make_float2(__uint_as_float(r[i * 4 + 0]), __uint_as_float(r[i * 4 + 1])), make_float2(b.x, b.y));
+    float2 v23 = fadd2(make_float2(__uint_as_float(r[i * 4 + 2]), __uint_as_float(r[i * 4 + 3])), make_float2(b.z, b.w));
     if (GELU) {
-      v0 = gelu_erf(v0);
-      v1 = gelu_erf(v1);
-      v2 = gelu_erf(v2);
-      v3 = gelu_erf(v3);
+      v01 = gelu_erf2(v01);
+      v23 = gelu_erf2(v23);
     }
-    pk[i * 2 + 0] = pack_bf16(v0, v1);
-    pk[i * 2 + 1] = pack_bf16(v2, v3);
+    pk[i * 2 + 0] = pack_bf16(v01.x, v01.y);
+    pk[i * 2 + 1] = pack_bf16(v23.x, v23.y);
   }
 }
 
@@ -272,6 +292,261 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// The same pipeline with tcgen05.mma.cta_group::2: a cluster of two CTAs (the two SMs of a TPC) computes a 256 x 256
+// output tile.  Each CTA stages its own 128 rows of A and only HALF of the W tile (128 of the 256 output columns); the
+// tensor cores of the pair exchange the W halves, so per flop each SM fills and reads a third less shared memory and
+// pulls a third less from L2 than with 128 x 256 single-CTA tiles (32 KiB instead of 48 KiB per k-block) -- under the
+// 1 kW power cap that is what separates this GEMM from the cuBLAS number.  The leader CTA (cluster rank 0) issues
+// every MMA; TMA loads of both CTAs complete on the leader's "full" barrier; tcgen05.commit multicasts the "stage
+// free" / "accumulator ready" arrivals to both CTAs; the follower's epilogue warps release the accumulator on the
+// leader's barrier through the cluster shared window.  Epilogues are the single-CTA ones (each CTA owns 128 rows).
+namespace pair {
+constexpr int STAGES2 = 5;
+constexpr int HALF_B_BYTES = 128 * BK * 2, STAGE2_BYTES = A_BYTES + HALF_B_BYTES;
+constexpr int OFF_STG2 = STAGES2 * STAGE2_BYTES, OFF_BAR2 = OFF_STG2 + EPI_WARPS * STG_BYTES;
+constexpr int SMEM2_BYTES = OFF_BAR2 + 256 + 1024;
+static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t IDESC2 = umma_idesc_bf16(2 * BM, BN, 0, 0);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address -> even CTA
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {  // whole warp, both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA tile load into THIS CTA's shared memory whose bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all previously issued MMAs of the pair have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const Params p) {
+  static_assert(EPI != ZK_EPI_PATCH_F32, "the patch-embedding epilogue stays on the single-CTA kernel");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);  // leader's copy is the live one
+  uint64_t* empty = full + STAGES2;                                // one per CTA
+  uint64_t* tfull = empty + STAGES2;                               // one per CTA
+  uint64_t* tempty = tfull + 2;                                    // leader's copy is the live one (2 x 8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // both CTAs' barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row tiles here
+  const int kblocks = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);  // both CTAs' tiles land on this barrier
+          uint8_t* sa = smem + stage * STAGE2_BYTES;
+          tma_load_2d_pair(sa, &tmA, &full[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
+          tma_load_2d_pair(sa + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN + (int)rank * 128);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+            const uint64_t a_desc = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t b_desc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC2, (kb | k) != 0);
+            umma_commit_pair(&empty[stage]);
+            if (kb == kblocks - 1) umma_commit_pair(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // which 128 accumulator columns
+    uint8_t* stg = smem + OFF_STG2 + (warp - 2) * STG_BYTES;  // this warp's 32 x 128 B staging tile (1024-B aligned)
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
+    int t = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      const int col_base = n_blk * BN + half * 128;
+      if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_ld_wait();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + i);
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, stg, col_base + c * 32, row0);
+            bulk_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_acc + c * 64, r0);
+          tmem_ld32(t_acc + c * 64 + 32, r1);
+          tmem_ld_wait();
+          uint32_t pk[32];
+          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r0, p.bias + col_base + c * 64,
+                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r1, p.bias + col_base + c * 64 + 32,
+                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), pk[i * 4 + 0], pk[i * 4 + 1], pk[i * 4 + 2],
+                         pk[i * 4 + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, col_base + c * 64, row0);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_leader(&tempty[acc]);
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // neither CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
+template <int EPI>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
+                       cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_done = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  ProfScope prof(prof_cls, stream);
+  gemm_pair_kernel<EPI><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
+  ZK_LAUNCH_CHECK("gemm_pair_kernel");
+  return 0;
+}
+}  // namespace pair
+
 template <int EPI>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                   cudaStream_t stream) {
@@ -332,6 +607,21 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
   const auto cls = [&](int by_epilogue) { return prof_cls >= 0 ? prof_cls : by_epilogue; };
+  // CTA-pair tiles for the large GEMMs (ZK_GEMM_PAIR: 0 = never, 1 = all but fc1, 2 = all).  fc1 stays on single-CTA
+  // tiles by default: its erf-GELU epilogue, not the mainloop, paces the tile, and the pair kernel's faster mainloop
+  // only lowers the clock it runs at.
+  static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 1;
+  if (use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2)) {
+    if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, BK))) return rc;  // half W tiles
+    p.num_m_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
+    switch (epilogue) {
+      case ZK_EPI_BIAS_BF16: return pair::launch_pair<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
+      case ZK_EPI_BIAS_GELU_BF16:
+        return pair::launch_pair<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
+      case ZK_EPI_BIAS_RESID_F32:
+        return pair::launch_pair<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, cls(K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT), stream);
+    }
+  }
   switch (epilogue) {
     case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
     case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
