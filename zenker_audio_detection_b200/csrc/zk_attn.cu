@@ -456,18 +456,21 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
     set_error("attention_bf16: batch %d x tokens %d is too large", batch, tokens);
     return ZK_ERR_SHAPE;
   }
-  static int poly = -1;  // share of exp2 evaluated on the FMA pipe: 0, 1 or 2 of every 4 pairs (ZK_ATTN_POLY overrides)
-  static int stagger = 1;
-  if (poly < 0) {
-    const char* sg = getenv("ZK_ATTN_STAGGER");
-    if (sg) stagger = atoi(sg);
-    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    ZK_CUDA(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  // share of exp2 evaluated on the FMA pipe: 0, 1 or 2 of every 4 pairs (ZK_ATTN_POLY), start offset of tile B
+  // (ZK_ATTN_STAGGER); read once (thread-safe function-local statics)
+  static const int poly = [] {
     const char* e = getenv("ZK_ATTN_POLY");
-    poly = e ? atoi(e) : 1;
-    if (poly < 0 || poly > 2) poly = 1;
-  }
+    const int v = e ? atoi(e) : 1;
+    return (v < 0 || v > 2) ? 1 : v;
+  }();
+  static const int stagger = [] {
+    const char* e = getenv("ZK_ATTN_STAGGER");
+    return e ? atoi(e) : 1;
+  }();
+  static unsigned long long attr_done[3] = {0, 0, 0};
+  const void* kernels[3] = {reinterpret_cast<const void*>(attn_kernel<0>), reinterpret_cast<const void*>(attn_kernel<1>),
+                            reinterpret_cast<const void*>(attn_kernel<2>)};
+  if ((rc = ensure_dynamic_smem(kernels[poly], SMEM_BYTES, &attr_done[poly]))) return rc;
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
   const int grid = items < num_sms() ? (int)items : num_sms();

@@ -273,6 +273,9 @@ struct ProfScope {  // counts one launch of class `cls`; brackets it with events
 };
 
 // ----------------------------------------------------------------------------- host helpers
+// Opt a kernel into `bytes` of dynamic shared memory once per DEVICE (the attribute belongs to the context, and the
+// library may be driven from several host threads): `done` is a per-kernel bit mask indexed by device ordinal.
+int ensure_dynamic_smem(const void* kernel, int bytes, unsigned long long* done);
 int device_check();  // 0 when the device is sm_100 and the tensor-map encoder is available
 int num_sms();
 // bf16 row-major 2-D [rows, cols] with row pitch `pitch_elems`, (box_rows x box_cols) box, 128-B swizzle.

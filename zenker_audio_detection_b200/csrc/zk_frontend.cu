@@ -261,12 +261,9 @@ __global__ void fill_pad_kernel(float* __restrict__ out, int batch, int first_ro
 }
 
 static int launch_fbank(const zk_fbank_plan* plan, Job job, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZK_CUDA(cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    ZK_CUDA(cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static unsigned long long attr_bulk = 0, attr_plain = 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fbank_kernel<true>), SMEM_BYTES, &attr_bulk)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fbank_kernel<false>), SMEM_BYTES, &attr_plain)) return rc;
   if (job.num_tiles <= 0) return 0;
   const bool bulk = (reinterpret_cast<uintptr_t>(job.wave) % 16 == 0) && (job.src_pitch % 4 == 0);
   long long grid = job.num_tiles < (long long)num_sms() ? job.num_tiles : (long long)num_sms();
@@ -558,11 +555,9 @@ static int run(const T* in, long long n_in, int channels, long long ch_pitch, co
     constexpr int KLEN = 2 * W + O, OB = DEC_THREADS * R, PAD = (4 - W % 4) % 4;                                \
     constexpr int NIN = (O * (OB - 1) + PAD + KLEN + 3) / 4 * 4;                                                \
     constexpr int SMEM = (2 * NIN + OB + (KLEN + 1) / 2 * 2) * 4 + 16;                                          \
-    static bool attr_done = false;                                                                              \
-    if (!attr_done) {                                                                                           \
-      ZK_CUDA(cudaFuncSetAttribute(decimate_kernel<T, O, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); \
-      attr_done = true;                                                                                         \
-    }                                                                                                           \
+    static unsigned long long attr_done = 0;                                                                    \
+    if (int rc_ = ensure_dynamic_smem(reinterpret_cast<const void*>(decimate_kernel<T, O, W, R>), SMEM, &attr_done)) \
+      return rc_;                                                                                               \
     long long blocks = (n_out + OB - 1) / OB;                                                                   \
     if (blocks > 2LL * sms) blocks = 2LL * sms;                                                                 \
     const int bulk_ok = std::is_same<T, float>::value && channels == 1 && (reinterpret_cast<uintptr_t>(in) & 15) == 0; \
@@ -574,11 +569,8 @@ static int run(const T* in, long long n_in, int channels, long long ch_pitch, co
   }
   if (new_ == 1 && orig == 3 && width == 19 && std::is_same<T, float>::value && channels == 1 &&
       (reinterpret_cast<uintptr_t>(in) & 15) == 0) {  // 48 kHz mono float32: the packed-FIR kernel
-    static bool attr3_done = false;
-    if (!attr3_done) {
-      ZK_CUDA(cudaFuncSetAttribute(decimate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
-      attr3_done = true;
-    }
+    static unsigned long long attr3_done = 0;
+    if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(decimate3_kernel), D3_SMEM, &attr3_done))) return rc;
     long long blocks = (n_out + D3_OB - 1) / D3_OB;
     if (blocks > 2LL * sms) blocks = 2LL * sms;
     ProfScope prof(ZK_K_RESAMPLE, stream);

@@ -517,11 +517,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int EPI>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                        cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI>), SMEM2_BYTES, &attr_done)) return rc;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   ProfScope prof(prof_cls, stream);
@@ -534,11 +531,8 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 template <int EPI>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                   cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<EPI>), SMEM_BYTES, &attr_done)) return rc;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope prof(prof_cls, stream);

@@ -131,6 +131,16 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, pitch_elems, box_rows, box_cols);
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes, unsigned long long* done) {
+  int dev = 0;
+  ZK_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return 0;
+  ZK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- profiler
 struct ProfRec {
   int cls;

@@ -255,11 +255,8 @@ int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, 
     set_error("attention_head_rows: %d tokens do not fit the score buffer", tokens);
     return ZK_ERR_SHAPE;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZK_CUDA(cudaFuncSetAttribute(attention_head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_head_rows_kernel), 200 * 1024, &attr_done)) return rc;
   ProfScope prof(ZK_K_TAIL, stream);
   attention_head_rows_kernel<<<dim3(AH_HEADS, batch), AH_THREADS, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q2), reinterpret_cast<const __nv_bfloat16*>(qkv),
