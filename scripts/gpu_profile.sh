@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 3 -c 2 -o gpurun_out/${tag}_attn -f $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 $CMD > gpurun_out/${tag}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 8 -c 5 -o gpurun_out/${tag}_gemm -f $CMD > gpurun_out/${tag}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 8 -c 6 -o gpurun_out/${tag}_gemm -f $CMD > gpurun_out/${tag}_ncu3.log 2>&1
 $CMD > gpurun_out/${tag}_plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"fbank_kernel|layernorm_kernel|decimate" -c 3 -o gpurun_out/${tag}_mem -f $CMD > gpurun_out/${tag}_ncu4.log 2>&1
 ls -la gpurun_out/ | tail -20

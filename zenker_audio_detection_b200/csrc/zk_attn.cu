@@ -219,7 +219,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
 template <int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int tokens,
-            int num_items, int qpairs, int stagger, long long* trace) {
+            int num_items, int qpairs, int stagger, long long* trace, int trace_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;          // [2] item parity
@@ -236,7 +236,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
   const int nkv = (tokens + BKV - 1) / BKV;
   const int my_items = ((int)blockIdx.x < num_items) ? (num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // optional timeline capture (zk_attention_trace): 128 slots per CTA, first item of each CTA
-  long long* tr = (trace && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
+  // trace_items: record only the end of every work item (slots 8 + it for tile A, 68 + it for tile B, it < 60)
+  long long* tr_it = (trace && trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
+  long long* tr = (trace && !trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
+  if (tr_it && threadIdx.x == 0) tr_it[1] = clock64();
   if (tr && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -431,6 +434,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         bulk_commit();
       }
       if (tracer && it == 0) tr[2] = clock64();
+      if (tr_it && quarter == 0 && lane == 0 && it < 60) tr_it[(t ? 68 : 8) + it] = clock64();
     }
     if ((warp & 3) == 0 && lane == 0) bulk_wait0();  // every output tile has landed before the CTA retires
   }
@@ -467,6 +471,7 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
     const char* e = getenv("ZK_ATTN_STAGGER");
     return e ? atoi(e) : 1;
   }();
+  static const int trace_items = getenv("ZK_ATTN_TRACE_ITEMS") ? atoi(getenv("ZK_ATTN_TRACE_ITEMS")) : 0;
   static unsigned long long attr_done[3] = {0, 0, 0};
   const void* kernels[3] = {reinterpret_cast<const void*>(attn_kernel<0>), reinterpret_cast<const void*>(attn_kernel<1>),
                             reinterpret_cast<const void*>(attn_kernel<2>)};
@@ -478,11 +483,11 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
   if ((rc = make_tmap_bf16_3d(&o, out, (uint64_t)batch, (uint64_t)tokens, HID, HID, (uint64_t)tokens * HID, 128, 64))) return rc;
   ProfScope prof(ZK_K_ATTENTION, stream);
   if (poly == 0)
-    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
+    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
   else if (poly == 1)
-    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
+    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
   else
-    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace);
+    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
 }

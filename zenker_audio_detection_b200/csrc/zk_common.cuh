@@ -286,6 +286,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // `rows` are clipped per slab, so a tile that overhangs the end of one slab never touches the next one.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t slabs, uint64_t rows, uint64_t cols,
                       uint64_t pitch_elems, uint64_t slab_pitch_elems, uint32_t box_rows, uint32_t box_cols);
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t slabs, uint64_t rows, uint64_t cols,
+                     uint64_t pitch_elems, uint64_t slab_pitch_elems, uint32_t box_rows, uint32_t box_cols);
 // same for fp32 (box_cols must be 32 = 128 B)
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                      uint32_t box_rows, uint32_t box_cols);

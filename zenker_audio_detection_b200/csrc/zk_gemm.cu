@@ -117,7 +117,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (EPI != ZK_EPI_PATCH_F32) tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -205,12 +205,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
       if constexpr (EPI == ZK_EPI_PATCH_F32) {
+        // rows of this warp: patches pr0 .. pr0 + 31 of window w0 unless the group straddles a window (or the end of
+        // the matrix); the common case goes through the staging tile and ONE TMA store per 32 x 32 block (the 3-D
+        // map addresses x as [window][token][768], token = 2 + patch), the straddling groups store row by row
+        const long long grow = (long long)row0;
+        const long long w0 = grow / p.aux_rows;
+        const int pr0 = (int)(grow - w0 * p.aux_rows);
+        const bool whole = pr0 + 32 <= p.aux_rows && grow + 32 <= p.M;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
           tmem_ld32(t_acc + c * 32, r);
           tmem_ld_wait();
-          patch_store(p, (long long)row0 + lane, col_base + c * 32, r);
+          if (!whole) {
+            patch_store(p, grow + lane, col_base + c * 32, r);
+            continue;
+          }
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+          const float4* pos4 = reinterpret_cast<const float4*>(p.aux + (long long)(2 + pr0 + lane) * p.N + col_base + c * 32);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + i);
+            const float4 o = __ldg(pos4 + i);
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x + o.x),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y + o.y),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z + o.z),
+                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w + o.w));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, stg, col_base + c * 32, 2 + pr0, (int)w0);
+            bulk_commit();
+          }
         }
       } else if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
         // 4 chunks of 32 fp32 columns: (acc + bias) -> staging -> TMA reduce-add into the residual stream
@@ -572,7 +602,11 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   } else if (epilogue == ZK_EPI_BIAS_RESID_F32) {
     if ((rc = make_tmap_f32_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)out_pitch, 32, 32))) return rc;
   } else {
-    tmC = tmA;  // unused by the patch epilogue
+    // patch embedding: x viewed as [windows][patches + 2 tokens][N]
+    const uint64_t windows = (uint64_t)((M + aux_rows - 1) / aux_rows);
+    if ((rc = make_tmap_f32_3d(&tmC, out, windows, (uint64_t)aux_rows + 2, (uint64_t)N, (uint64_t)N,
+                               (uint64_t)(aux_rows + 2) * N, 32, 32)))
+      return rc;
   }
   Params p;
   p.bias = bias;

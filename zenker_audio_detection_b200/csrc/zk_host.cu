@@ -126,6 +126,28 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t slabs, uint64
   }
   return 0;
 }
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t slabs, uint64_t rows, uint64_t cols,
+                     uint64_t pitch_elems, uint64_t slab_pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+  int rc = device_check();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_elems * 4) % 16 || (slab_pitch_elems * 4) % 16 || box_cols != 32 ||
+      box_rows > 256) {
+    set_error("make_tmap_f32_3d: bad alignment/box");
+    return ZK_ERR_ARG;
+  }
+  cuuint64_t gdim[3] = {cols, rows, slabs};
+  cuuint64_t gstr[2] = {pitch_elems * 4, slab_pitch_elems * 4};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32 3d) failed (%d)", (int)r);
+    return ZK_ERR_INTERNAL;
+  }
+  return 0;
+}
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                      uint32_t box_rows, uint32_t box_cols) {
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, pitch_elems, box_rows, box_cols);
