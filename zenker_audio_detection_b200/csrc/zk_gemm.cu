@@ -549,8 +549,35 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI>), SMEM2_BYTES, &attr_done)) return rc;
+  // persistent grid = the number of CTA pairs the device can hold at once (a TPC with one usable SM cannot host a
+  // pair, so this may be less than num_sms / 2); asked from the runtime once per device
+  static int resident[64] = {0};
+  int dev = 0;
+  ZK_CUDA(cudaGetDevice(&dev));
+  int cap = __atomic_load_n(&resident[dev & 63], __ATOMIC_ACQUIRE);
+  if (cap == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (num_sms() / 2));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / 2;
+    }
+    cap = n < num_sms() / 2 ? n : num_sms() / 2;
+    __atomic_store_n(&resident[dev & 63], cap, __ATOMIC_RELEASE);
+    if (getenv("ZK_DEBUG")) fprintf(stderr, "zk: %d resident CTA pairs for gemm_pair_kernel<%d>\n", cap, EPI);
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  const int clusters = tiles < cap ? tiles : cap;
   ProfScope prof(prof_cls, stream);
   gemm_pair_kernel<EPI><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_pair_kernel");
