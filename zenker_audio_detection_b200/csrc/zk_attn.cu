@@ -118,27 +118,33 @@ struct SoftmaxState {
 // by more than 2^8 is the accumulator rescaled and the block redone from the scores still held in registers.  That
 // keeps a warp's MUFU demand uniform over the block instead of 0 % during a max phase and 100 % after it, which is
 // what lets the two softmax warps of a scheduler share the MUFU pipe without phase locking.
-template <bool RAGGED, bool FIRST, int POLY>
+//
+// W = how many key columns of the block are processed at all: a ragged last block with kmax <= 64 valid keys (tokens =
+// 1214 leaves 62) only takes the lower half of S, writes the lower half of P, and the issuer shortens P V to W keys.
+template <bool RAGGED, bool FIRST, int POLY, int W = 128>
 __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_valid, uint32_t t_s, uint32_t t_o, uint32_t t_p,
                                               uint64_t* s_free, uint64_t* pv_done, SoftmaxState& st, long long* trj) {
   uint32_t s[128];
+  static_assert(W == 64 || W == 128, "key columns per block");
   tmem_ld32_at<0>(t_s, s);
   tmem_ld32_at<32>(t_s + 32, s);
-  tmem_ld32_at<64>(t_s + 64, s);
-  tmem_ld32_at<96>(t_s + 96, s);
+  if (W == 128) {
+    tmem_ld32_at<64>(t_s + 64, s);
+    tmem_ld32_at<96>(t_s + 96, s);
+  }
   tmem_ld_wait();
   tc_fence_before();
   mbar_arrive(s_free);  // the score buffer may be overwritten by S(j+1) from here on
   if (trj) trj[3] = clock64();
   if (RAGGED) {
 #pragma unroll
-    for (int i = 0; i < 128; ++i)
+    for (int i = 0; i < W; ++i)
       if (i >= kmax) s[i] = 0xff800000u;  // -inf
   }
   if (FIRST) {
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 128; i += 8) {
+    for (int i = 0; i < W; i += 8) {
       mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
       mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
       mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
@@ -159,7 +165,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
     lba = make_float2(0.f, 0.f);
     lbb = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < W / 32; ++c) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -219,7 +225,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
 template <int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int tokens,
-            int num_items, int qpairs, int stagger, long long* trace, int trace_items) {
+            int num_items, int qpairs, int stagger, int half_keys, long long* trace, int trace_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;          // [2] item parity
@@ -351,11 +357,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         if (elect_one()) {
           const uint32_t j = g % (uint32_t)nkv;
           const uint32_t sv = smem_u32(smem + OFF_KV + (g % KV_STAGES) * 2 * TILE_BYTES + TILE_BYTES);
+          // a last block with at most 64 valid keys only has the lower half of P written (softmax_block W = 64)
+          const int ksteps = (tokens - (int)j * BKV <= half_keys) ? BKV / 32 : BKV / 16;
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             // A = P_t: 16 keys = 8 TMEM columns; B = V_j: 16 keys = 16 rows of 128 B (MN-major)
             const uint64_t v_desc = umma_desc_sw128(sv + k * 16 * 128, 1024, 1024);
-            umma_bf16_ts(d_o, a_p + k * 8, v_desc, IDESC_O, (j | (uint32_t)k) != 0);
+            if (k < ksteps) umma_bf16_ts(d_o, a_p + k * 8, v_desc, IDESC_O, (j | (uint32_t)k) != 0);
           }
           umma_commit(&pv_done[t]);
           umma_commit(&kv_empty[g % KV_STAGES]);  // K_g / V_g are dead once both tiles' P V have executed (count 2)
@@ -389,7 +397,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         tc_fence_after();
         if (trj) trj[1] = clock64();
         const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
-        if (kmax < BKV) {
+        if (kmax <= half_keys) {
+          if (j == 0)
+            softmax_block<true, true, POLY, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+          else
+            softmax_block<true, false, POLY, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+        } else if (kmax < BKV) {
           if (j == 0)
             softmax_block<true, true, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
@@ -471,6 +484,7 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
     const char* e = getenv("ZK_ATTN_STAGGER");
     return e ? atoi(e) : 1;
   }();
+  static const int half_keys = (getenv("ZK_ATTN_HALF") && atoi(getenv("ZK_ATTN_HALF")) == 0) ? 0 : BKV / 2;
   static const int trace_items = getenv("ZK_ATTN_TRACE_ITEMS") ? atoi(getenv("ZK_ATTN_TRACE_ITEMS")) : 0;
   static unsigned long long attr_done[3] = {0, 0, 0};
   const void* kernels[3] = {reinterpret_cast<const void*>(attn_kernel<0>), reinterpret_cast<const void*>(attn_kernel<1>),
@@ -483,11 +497,11 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
   if ((rc = make_tmap_bf16_3d(&o, out, (uint64_t)batch, (uint64_t)tokens, HID, HID, (uint64_t)tokens * HID, 128, 64))) return rc;
   ProfScope prof(ZK_K_ATTENTION, stream);
   if (poly == 0)
-    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
+    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
   else if (poly == 1)
-    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
+    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
   else
-    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, trace, trace_items);
+    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
 }
