@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 LIB_NAME = "libzk_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
+# ZK_B200_LIB points at another build of the same library (same-box A/B runs of a kernel change); default: in-tree
+LIB_PATH = os.environ.get("ZK_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 AST_LAYERS = 12
 
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32 = 0, 1, 2, 3

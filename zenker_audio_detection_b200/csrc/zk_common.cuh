@@ -65,6 +65,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with an explicit suspend-time hint (ns): without one the thread comes back after a few tens of cycles and a
+// waiting warp spends issue slots on its polling loop
+__device__ __forceinline__ bool mbar_try_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+      : "memory");
+  return ok != 0;
+}
 // Non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is still pending).
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -83,7 +96,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   uint32_t n = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_long(bar, parity)) {
     if ((++n & 0x3ff) == 0 && clock64() - t0 > 8000000000LL) {
       printf("zk: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%p parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, (void*)bar, parity);
