@@ -19,6 +19,10 @@ resample.npz         ``torchaudio.functional.resample`` 48k->16k and 44.1k->16k 
                      synthetic recording (exactly what ``ref.load_audio`` does after decode).
 ast_cfg1.npz         ``ref.forward_probs`` probabilities and HF logits of the conditioned
                      random-init Stage-1 / Stage-2 models for the first 16 cfg1 windows.
+cache_golden.json,   ``refc.get_fx_fingerprint`` / ``build_cache_path`` / ``build_base_metadata`` for fixed files
+cache_ref_bundle.pt  (path, size, mtime), and a feature bundle WRITTEN BY ``refc.load_or_compute_features`` (HF
+                     extractor, max_length 16 to keep it small); also checks that the reference LOADS a bundle
+                     written by ``zenker_audio_detection_b200.cache`` instead of recomputing.
 cascade_60s.npz      the whole reference cascade (ref.window_audio -> ref.forward_probs ->
                      gate -> ref.forward_probs -> ref.summarize_stage_outputs) on a 60-s
                      48 kHz synthetic recording (119 windows).
@@ -260,13 +264,77 @@ def gold_cascade_60s():
     print("cascade_60s", len(windows), len(idx), summ)
 
 
+CACHE_FIXTURE_DIR = "/tmp/zk_cache_golden"  # absolute on purpose: the cache key hashes the absolute path (refc:97-100)
+
+
+def make_cache_fixture_file(name, size, mtime):
+    """A fake recording with a fixed absolute path, size and mtime (the three things the cache key depends on)."""
+    d = os.path.join(CACHE_FIXTURE_DIR, "audio")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, name)
+    with open(path, "wb") as f:
+        f.write(bytes((i * 37 + 11) & 0xFF for i in range(size)))
+    os.utime(path, (mtime, mtime))
+    return path
+
+
+def gold_cache():
+    import shutil
+
+    from transformers import ASTFeatureExtractor
+
+    from zenker_audio_detection_b200 import cache as zcache
+
+    shutil.rmtree(CACHE_FIXTURE_DIR, ignore_errors=True)
+    doc = {"fixture_dir": CACHE_FIXTURE_DIR, "files": [], "keys": []}
+    fx_full = T.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
+    fx_small = ASTFeatureExtractor(max_length=16, mean=synth.STAGE2_MEAN, std=synth.STAGE2_STD)
+    doc["fingerprints"] = {"stage1_default": refc.get_fx_fingerprint(fx_full), "small": refc.get_fx_fingerprint(fx_small)}
+    doc["fx_dicts"] = {"stage1_default": fx_full.to_dict(), "small": fx_small.to_dict()}
+    cache_dir = os.path.join(CACHE_FIXTURE_DIR, "cache")
+    for name, size, mtime in [("rec_A.wav", 4321, 1700000000), ("P017 swallow.long.wav", 99, 1234567890)]:
+        path = make_cache_fixture_file(name, size, mtime)
+        doc["files"].append({"name": name, "size": size, "mtime": mtime})
+        for (w, h, n) in [(1.0, 0.5, 7), (0.5, 0.25, 1199), (2.0, 1.0, 1)]:
+            for fxname in ("stage1_default", "small"):
+                fp = doc["fingerprints"][fxname]
+                doc["keys"].append({"file": name, "window_sec": w, "hop_sec": h, "num_windows": n, "fx": fxname,
+                                    "cache_path": refc.build_cache_path(cache_dir, path, w, h, 16000, fp),
+                                    "base_metadata": refc.build_base_metadata(path, w, h, n, 16000, fp)})
+    # (A) a bundle written by the reference, committed as a fixture
+    path = os.path.join(CACHE_FIXTURE_DIR, "audio", "rec_A.wav")
+    windows = list(synth.cfg1_windows(64)[:4])
+    with contextlib.redirect_stdout(io.StringIO()):
+        feats = refc.load_or_compute_features(path, windows, fx_small, 1.0, 0.5, 2, cache_dir, False, False, "stage1")
+    written = refc.build_cache_path(cache_dir, path, 1.0, 0.5, 16000, doc["fingerprints"]["small"])
+    assert os.path.exists(written) and tuple(feats.shape) == (4, 16, 128)
+    shutil.copy(written, os.path.join(GOLD, "cache_ref_bundle.pt"))
+    doc["ref_bundle"] = {"file": "cache_ref_bundle.pt", "cache_path": written, "num_windows": 4, "fx": "small",
+                         "feature_shape": list(feats.shape), "feature_sum": float(feats.double().sum())}
+    # (B) a bundle written by OUR module must be loaded (not recomputed) by the reference
+    path_b = os.path.join(CACHE_FIXTURE_DIR, "audio", "P017 swallow.long.wav")
+    fp = zcache.get_fx_fingerprint(fx_small)
+    ours = torch.arange(3 * 16 * 128, dtype=torch.float32).reshape(3, 16, 128) * 1e-3
+    os.makedirs(cache_dir, exist_ok=True)
+    zcache.save_bundle(zcache.build_cache_path(cache_dir, path_b, 1.0, 0.5, 16000, fp),
+                       zcache.build_base_metadata(path_b, 1.0, 0.5, 3, 16000, fp), ours)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        got = refc.load_or_compute_features(path_b, windows[:3], fx_small, 1.0, 0.5, 2, cache_dir, False, False, "stage2")
+    doc["reference_loaded_our_bundle"] = bool("Loaded" in out.getvalue() and torch.equal(got, ours))
+    assert doc["reference_loaded_our_bundle"], out.getvalue()
+    with open(os.path.join(GOLD, "cache_golden.json"), "w") as f:
+        json.dump(doc, f, indent=1, sort_keys=True)
+    print("cache golden:", len(doc["keys"]), "keys; reference loaded our bundle:", doc["reference_loaded_our_bundle"])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-ast", action="store_true")
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "ast", "astplain", "cascade60"]
+    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "cache", "ast", "astplain", "cascade60"]
     if "windows" in todo:
         gold_windows()
     if "cascade" in todo:
@@ -275,6 +343,8 @@ if __name__ == "__main__":
         gold_fx()
     if "resample" in todo:
         gold_resample()
+    if "cache" in todo:
+        gold_cache()
     if not a.skip_ast:
         if "ast" in todo:
             gold_ast()

@@ -13,7 +13,7 @@ def _ref(qkv, B, T):
 
 
 @pytest.mark.parametrize("B,T,scale", [(2, 1214, 1.0), (1, 128, 1.0), (1, 129, 1.0), (3, 300, 3.0), (1, 62, 1.0),
-                                       (1, 1214, 6.0),
+                                       (1, 1214, 6.0), (2, 192, 1.0), (1, 193, 2.0),  # last key block of exactly 64 / 65 keys (half-width path)
                                        (16, 1214, 2.0), (40, 200, 4.0)])  # > 148 work items: persistent CTAs walk several
 def test_attention(B, T, scale):
     from zenker_audio_detection_b200 import ops

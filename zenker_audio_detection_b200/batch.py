@@ -94,6 +94,11 @@ def build_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--stage2-threshold", type=float, default=0.5)
     ap.add_argument("--stage1-forward-min-prob", type=float)
     ap.add_argument("--stage2-argmax", action="store_true")
+    ap.add_argument("--feature-cache-dir", default=None,
+                    help="reuse / fill the reference's per-recording feature bundles (refc:84-192); default: no cache, "
+                         "the fused path recomputes the fbank")
+    ap.add_argument("--disable-cache", action="store_true")
+    ap.add_argument("--refresh-cache", action="store_true")
     ap.add_argument("--extra", help="accepted for compatibility; ignored")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--dry-run", action="store_true")
@@ -150,7 +155,7 @@ def run(args, rank: int = 0, world: int = 1) -> int:
     import torch
     from transformers import ASTConfig
 
-    from . import results
+    from . import cache as zcache, results
     from .fx import ZenkerASTFeatureExtractor
     from .model import ZenkerASTForAudioClassification
     from .pipeline import TwoStagePipeline
@@ -171,17 +176,27 @@ def run(args, rank: int = 0, world: int = 1) -> int:
                             stage1_threshold=thr1, stage2_threshold=thr2,
                             stage1_forward_min_prob=args.stage1_forward_min_prob, stage2_argmax=args.stage2_argmax,
                             device=device)
+    cache_dir = None  # refc:428-430
+    if not args.disable_cache and args.feature_cache_dir:
+        cache_dir = os.path.abspath(args.feature_cache_dir)
     failures = 0
     for pid, files in mine:
         try:
             summaries = []
             for path in files:
                 samples, sr = wavio.read(path)
-                summaries.append(pipe.run_waveform(samples, sr).summary)
+                if cache_dir:  # refc:433-507 on the reference's feature bundles
+                    audio = pipe.resample_to_device(samples, sr)
+                    windows = zcache.window_audio(audio, args.window_sec, args.hop_sec)
+                    summaries.append(zcache.run_recording_cached(pipe, path, windows, cache_dir, False,
+                                                                 args.refresh_cache).summary)
+                else:
+                    summaries.append(pipe.run_waveform(samples, sr).summary)
             doc = results.build_document(s1_root, s2_root, args.window_sec, args.hop_sec, args.batch_size, thr1, files,
                                          summaries, variant="cached", stage2_threshold=thr2,
                                          stage1_forward_min_prob=args.stage1_forward_min_prob,
-                                         stage2_argmax=args.stage2_argmax, feature_cache_dir=None, disable_cache=True)
+                                         stage2_argmax=args.stage2_argmax, feature_cache_dir=cache_dir,
+                                         disable_cache=cache_dir is None)
             results.write_json(doc, os.path.join(out_dir, f"{pid}_2stage.json"))
             print(f"[DONE] {pid} OK")
         except Exception as e:  # noqa: BLE001 - ref batch:286-289: log and continue with the next patient

@@ -124,16 +124,19 @@ class TwoStagePipeline:
         summary = cascade.summarize_stage_outputs(s1, idx, s2, self.thr2, self.stage2_argmax)
         return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary)
 
-    def run_waveform(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> RecordingResult:
-        """``waveform``: host (or device) ``(channels, n)`` / ``(n,)`` float32, or ``(n, channels)`` int16 PCM."""
+    def resample_to_device(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> torch.Tensor:
+        """ref:53-59 (``load_audio`` after the decode): H2D, channel mean, resample -> CUDA float32 mono 16 kHz."""
         w = torch.from_numpy(np.ascontiguousarray(waveform)) if isinstance(waveform, np.ndarray) else waveform
         if w.dtype not in (torch.float32, torch.int16):
             w = w.to(torch.float32)
         with torch.cuda.device(self.device):
             if not w.is_cuda:
                 w = (w if w.is_pinned() else w.pin_memory()).to(self.device, non_blocking=True)
-            audio = ops.resample(w, int(sample_rate), SAMPLING_RATE)
-        return self.run_audio16k(audio)
+            return ops.resample(w, int(sample_rate), SAMPLING_RATE)
+
+    def run_waveform(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> RecordingResult:
+        """``waveform``: host (or device) ``(channels, n)`` / ``(n,)`` float32, or ``(n, channels)`` int16 PCM."""
+        return self.run_audio16k(self.resample_to_device(waveform, sample_rate))
 
     def run_patient(self, waveforms: Sequence[Union[np.ndarray, torch.Tensor]], sample_rates: Sequence[int],
                     names: Optional[Sequence[str]] = None) -> Dict[str, Any]:
