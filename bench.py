@@ -336,7 +336,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int((n_e2e // max(1, world) // args.steps) * 12 + 4 + (k // max(1, world) // args.steps) * 12)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BIAS_GELU> (fc1, M=batch*1214, N=3072, K=768)",
+        "roofline": {"bound": "tensor", "kernel": "pair::gemm_pair_kernel<BIAS_GELU> (fc1, M=batch*1214, N=3072, K=768)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "traffic_note": (f"dram read+write of one {traffic_rows}-row launch, ncu --set full "
                                                           "(profiles/roofline_traffic.json)") if traffic else None,

@@ -646,10 +646,10 @@ int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long l
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
   const auto cls = [&](int by_epilogue) { return prof_cls >= 0 ? prof_cls : by_epilogue; };
-  // CTA-pair tiles for the large GEMMs (ZK_GEMM_PAIR: 0 = never, 1 = all but fc1, 2 = all).  fc1 stays on single-CTA
-  // tiles by default: its erf-GELU epilogue, not the mainloop, paces the tile, and the pair kernel's faster mainloop
-  // only lowers the clock it runs at.
-  static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 1;
+  // CTA-pair tiles for the large GEMMs (ZK_GEMM_PAIR: 0 = never, 1 = all but fc1, 2 = all, the default).  With the
+  // two-MUFU GELU the fc1 epilogue paced its tile and pair tiles did not pay; with the one-MUFU form they do
+  // (0.586 against 0.606 ms at M = 155 392 on the same box).
+  static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 2;
   if (use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2)) {
     if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, BK))) return rc;  // half W tiles
     p.num_m_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
