@@ -164,3 +164,26 @@ def test_cfg4_results_do_not_depend_on_order_or_rank():
     for rid in a:
         for x, y in zip(a[rid], b[rid]):
             assert np.array_equal(x, y)
+
+
+def test_cfg5_batch32_forward_is_batch_invariant_and_matches_the_fp32_oracle():
+    """cfg5: (32, 1024, 128) features ~ N(0, 0.5), seed 5005, 1214 tokens, bf16 weights.  The
+    32-window forward equals four 8-window forwards and thirty-two single-window forwards bit for bit (tile shapes do
+    not depend on the batch), and agrees with the fp32 oracle (HF's arithmetic restated, oracle/numerics.py) within the
+    bf16 tolerance of north_star on a plain random init."""
+    from oracle import numerics
+    from zenker_audio_detection_b200 import ops, synth
+
+    g = torch.Generator(device="cuda").manual_seed(5005)
+    feats = torch.randn(32, 1024, 128, device="cuda", generator=g) * 0.5
+    sd = synth.random_state_dict(31, qk_gain=1.0)
+    m = ops.AstModel(sd)
+    full = m.forward_features(feats)
+    assert full.shape == (32, 2) and full.dtype == torch.float32 and bool(torch.isfinite(full).all())
+    by8 = torch.cat([m.forward_features(feats[i:i + 8]) for i in range(0, 32, 8)])
+    by1 = torch.cat([m.forward_features(feats[i:i + 1]) for i in range(32)])
+    assert torch.equal(full, by8) and torch.equal(full, by1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.inference_mode():
+        ref = numerics.ast_forward({k: v.cuda() for k, v in sd.items()}, feats[:4])
+    assert (full[:4] - ref).abs().max().item() <= 1e-2
