@@ -200,6 +200,33 @@ def calibrate_gate(pipe, sd1, wave_dev, fraction, device):
     return shift
 
 
+def cpu_secondary(windows):
+    """the reference's front end on the host cores, bounded samples (a few seconds in all):
+    HF ASTFeatureExtractor over 64 windows, torchaudio kaldi.fbank over 10 min of 16 kHz audio (1/6 of cfg3),
+    torchaudio resample 48 -> 16 kHz over 2 min (1/5 of cfg2); GB/s are the algorithmic bytes of SURVEY.md 8d."""
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import synth
+
+    out = {"cores": torch.get_num_threads()}
+    fx = thirdparty.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
+    w = [np.ascontiguousarray(x) for x in windows[:64]]
+    t0 = time.perf_counter()
+    fx(w, sampling_rate=16000, return_tensors="pt")
+    out["fx_windows_per_s"] = len(w) / (time.perf_counter() - t0)
+    n = 9_600_000
+    wave = (np.random.default_rng(3003).standard_normal(n) * 0.05).astype(np.float32)
+    t0 = time.perf_counter()
+    fb = thirdparty.kaldi_fbank(wave)
+    dt = time.perf_counter() - t0
+    out["fbank_gb_per_s"] = (4.0 * n + 512.0 * fb.shape[0]) / dt / 1e9
+    rec = synth.recording(120.0, 48000, seed=2002)
+    t0 = time.perf_counter()
+    a = thirdparty.resample(rec, 48000, 16000)
+    dt = time.perf_counter() - t0
+    out["resample_gb_per_s"] = (4.0 * rec.shape[-1] + 4.0 * a.shape[-1]) / dt / 1e9
+    return out
+
+
 def secondary_metrics(device, peaks, engine=None):
     """The other two quantities BASELINE.json's metric names, measured outside the timed region on rank 0: the
     continuous fbank over 1 h of 16 kHz audio (cfg3; algorithmic bytes 4 n + 512 m) and the 48 -> 16 kHz
@@ -364,6 +391,7 @@ def run_ours(args):
             v, cores, desc, _ = cpu_reference_windows_per_s(glue.window_audio(audio, 1.0, 0.5), k / max(1, n),
                                                             seconds_budget=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            line["cpu_baseline"]["secondary"] = cpu_secondary(glue.window_audio(audio, 1.0, 0.5))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
