@@ -61,23 +61,22 @@ __device__ __forceinline__ void patch_store(const Params& p, long long row, int 
 }
 
 // erf-GELU (HF "gelu", activations.py) for two values at once with ONE MUFU op per value: with a = |x|,
-//     erfc(a / sqrt2) / 2 = 2^P(a),  P = degree-7 minimax fit of log2(erfc(a / sqrt2) / 2) on [0, 7.07]
-// (relative error of 2^P: 1.2e-5; beyond 7.07 the term is < 1e-12), and gelu(x) = max(x, 0) - a * 2^P(a), which covers
-// both signs because x Phi(x) = x - x erfc(x / sqrt2) / 2 for x >= 0 and = -a erfc(a / sqrt2) / 2 for x < 0.
-// Against the exact function in fp32: max abs error 1.4e-6, max relative error 1.4e-5 -- two orders below the bf16
-// rounding of the result.  The Horner chain runs on the packed pipe (7 FFMA2 per pair); 7.5 instructions and one
-// ex2 per value instead of 18 and two (rcp + ex2) for Abramowitz-Stegun 7.1.26, which is what keeps the fc1 epilogue
-// (32 768 values per tile on a 16-lane MUFU pipe) under the MMA time of its tile.
+//     erfc(a / sqrt2) / 2 = 2^P(a),  P = degree-5 weighted least-squares fit of log2(erfc(a / sqrt2) / 2) on [0, 7.07]
+// (beyond 7.07 the term is < 1e-12), and gelu(x) = max(x, 0) - a * 2^P(a), which covers both signs because
+// x Phi(x) = x - x erfc(x / sqrt2) / 2 for x >= 0 and = -a erfc(a / sqrt2) / 2 for x < 0.  The fit is weighted by
+// a exp(-0.55 a^2), i.e. by how much an error of P moves the result; against the exact function, evaluated in fp32:
+// max abs error 6.6e-7, max error relative to max(|gelu|, 1e-3) 4.7e-4 -- an order below the bf16 rounding of the
+// result (3.9e-3).  The Horner chain runs on the packed pipe (5 FFMA2 per pair); 6.5 instructions and one ex2 per value
+// instead of 18 and two (rcp + ex2) for Abramowitz-Stegun 7.1.26: the fc1 epilogue is 32 768 values per tile, and under
+// the power cap every instruction it issues is clock taken from the tensor pipe.
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 a = make_float2(fminf(fabsf(x.x), 7.0710678f), fminf(fabsf(x.y), 7.0710678f));
-  float2 p = ffma2(a, make_float2(-1.5859452560107457e-06f, -1.5859452560107457e-06f),
-                   make_float2(5.6180440878961235e-05f, 5.6180440878961235e-05f));
-  p = ffma2(p, a, make_float2(-0.0008844065596349537f, -0.0008844065596349537f));
-  p = ffma2(p, a, make_float2(0.008314338512718678f, 0.008314338512718678f));
-  p = ffma2(p, a, make_float2(-0.0535459965467453f, -0.0535459965467453f));
-  p = ffma2(p, a, make_float2(-0.45888257026672363f, -0.45888257026672363f));
-  p = ffma2(p, a, make_float2(-1.1510944366455078f, -1.1510944366455078f));
-  p = ffma2(p, a, make_float2(-1.000004768371582f, -1.000004768371582f));
+  float2 p = ffma2(a, make_float2(-0.00047368594096042216f, -0.00047368594096042216f),
+                   make_float2(0.007084728218615055f, 0.007084728218615055f));
+  p = ffma2(p, a, make_float2(-0.05182575806975365f, -0.05182575806975365f));
+  p = ffma2(p, a, make_float2(-0.4599885642528534f, -0.4599885642528534f));
+  p = ffma2(p, a, make_float2(-1.150799036026001f, -1.150799036026001f));
+  p = ffma2(p, a, make_float2(-1.0000325441360474f, -1.0000325441360474f));
   return make_float2(fmaf(-fabsf(x.x), fast_exp2(p.x), fmaxf(x.x, 0.f)), fmaf(-fabsf(x.y), fast_exp2(p.y), fmaxf(x.y, 0.f)));
 }
 
