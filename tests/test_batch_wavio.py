@@ -148,3 +148,26 @@ def test_patched_torchaudio_load_and_info(tmp_path):
         assert tuple(mono.shape) == (1, 3000)
     finally:
         compat.unpatch_torchaudio()
+
+
+def test_wav_prefetcher_keeps_order_and_reraises():
+    from zenker_audio_detection_b200.batch import WavPrefetcher
+
+    calls = []
+
+    def reader(path):
+        calls.append(path)
+        if path == "bad":
+            raise ValueError("not a RIFF file")
+        return (path.upper(), 16000)
+
+    pf = WavPrefetcher(["a", "bad", "c", "d"], reader=reader)
+    assert pf.get("a") == ("A", 16000)
+    with pytest.raises(ValueError, match="RIFF"):
+        pf.get("bad")            # the failure of one file surfaces at that file ...
+    assert pf.get("c") == ("C", 16000)  # ... and the next ones still come
+    assert pf.get("zzz") == ("ZZZ", 16000)  # out of order: read synchronously, prefetch of "d" untouched
+    assert pf.get("d") == ("D", 16000)
+    assert pf.get("a") == ("A", 16000)  # exhausted: synchronous
+    pf.close()
+    assert calls.count("d") == 1 and calls[:3] == ["a", "bad", "c"]

@@ -76,6 +76,38 @@ def default_model_root(stage: int, fold: int) -> str:
     return os.path.join(os.getcwd(), "runs", f"ast_classifier_stage{stage}", f"fold{fold}", "best")
 
 
+class WavPrefetcher:
+    """Decodes the next recording on a host thread while the GPU works on the current one (a 10-minute stereo PCM16
+    file is 115 MB: ~60 ms from NVMe, ~12 % of the 0.46 s the cascade takes).  ``get(path)`` returns what
+    ``wavio.read(path)`` returns and re-raises its exception; paths must be requested in the order given."""
+
+    def __init__(self, paths: Sequence[str], reader=wavio.read):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._paths, self._reader, self._next = list(paths), reader, 0
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._pending = None
+        self._submit()
+
+    def _submit(self) -> None:
+        self._pending = None
+        if self._next < len(self._paths):
+            self._pending = (self._paths[self._next], self._pool.submit(self._reader, self._paths[self._next]))
+            self._next += 1
+
+    def get(self, path: str):
+        if self._pending is None or self._pending[0] != path:
+            return self._reader(path)  # out of order (or exhausted): read synchronously
+        fut = self._pending[1]
+        try:
+            return fut.result()
+        finally:
+            self._submit()
+
+    def close(self) -> None:
+        self._pool.shutdown(wait=False, cancel_futures=True)
+
+
 def build_arg_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser(description="Two-stage window inference over every patient of a fold (B200, in process).")
     ap.add_argument("--fold", type=int, required=True)
@@ -180,11 +212,12 @@ def run(args, rank: int = 0, world: int = 1) -> int:
     if not args.disable_cache and args.feature_cache_dir:
         cache_dir = os.path.abspath(args.feature_cache_dir)
     failures = 0
+    wavs = WavPrefetcher([p for _, files in mine for p in files])
     for pid, files in mine:
         try:
             summaries = []
             for path in files:
-                samples, sr = wavio.read(path)
+                samples, sr = wavs.get(path)
                 if cache_dir:  # refc:433-507 on the reference's feature bundles
                     audio = pipe.resample_to_device(samples, sr)
                     windows = zcache.window_audio(audio, args.window_sec, args.hop_sec)
@@ -202,6 +235,7 @@ def run(args, rank: int = 0, world: int = 1) -> int:
         except Exception as e:  # noqa: BLE001 - ref batch:286-289: log and continue with the next patient
             failures += 1
             print(f"[ERROR] patient {pid}: {type(e).__name__}: {e}")
+    wavs.close()
     print("Batch complete." if world == 1 else f"Batch complete (rank {rank}).")
     return failures
 
