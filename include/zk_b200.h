@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZK_ABI_VERSION 1
+#define ZK_ABI_VERSION 2
 
 typedef void* zk_stream_t; /* cudaStream_t */
 
@@ -97,9 +97,20 @@ int zk_fx_contract_f32(const zk_fbank_plan* plan, const float* d_windows, int ba
  *     transformer.py:403-451) for the AST-base geometry (hidden 768, 12 layers, 12 heads, MLP 3072,
  *     patch 16, strides 10/10, 128 mel x max_length frames, LayerNorm eps from config).
  *     Weights are given as fp32 DEVICE pointers in HF layout (nn.Linear weight = [out][in]); the
- *     model handle keeps bf16 copies (QKV fused) plus fp32 biases / LayerNorm / position table.
+ *     model handle keeps 16-bit copies (QKV fused) plus fp32 biases / LayerNorm / position table.
+ *
+ *     Two precisions share one handle:
+ *       ZK_PRECISION_FAST     every GEMM / attention operand is ONE 16-bit value (operand_format: fp16 by default,
+ *                             11 significant bits; bf16, 8 bits, selectable), fp32 accumulation; the throughput path.
+ *       ZK_PRECISION_RECHECK  every operand is TWO fp16 planes (x = hi + lo, 22 bits) and every contraction adds the
+ *                             products lo*hi + hi*lo + hi*hi: fp32-class logits (a few 1e-6 from an fp32 CPU forward)
+ *                             at ~3.5x the time.  The cascade routes the windows whose fast logits fall within eps of
+ *                             a decision threshold through it BEFORE gating (ref:312-320 gates on exact fp32
+ *                             probabilities), so thresholded decisions equal the reference's.
  * ------------------------------------------------------------------------------------------ */
 #define ZK_AST_LAYERS 12
+enum zk_operand_format { ZK_FMT_BF16 = 0, ZK_FMT_F16 = 1 };
+enum zk_precision { ZK_PRECISION_FAST = 0, ZK_PRECISION_RECHECK = 1 };
 typedef struct zk_ast_layer_weights {
   const float *ln1_w, *ln1_b;     /* layernorm_before */
   const float *q_w, *q_b;         /* attention.attention.query  [768][768], [768] */
@@ -116,6 +127,7 @@ typedef struct zk_ast_weights {
   int32_t max_length;   /* frames per window the position table was built for (1024) */
   int32_t num_labels;   /* 2 */
   float ln_eps;         /* 1e-12 */
+  int32_t operand_format; /* zk_operand_format of the FAST path (the re-check planes are always fp16) */
   const float* cls_token;     /* [768] */
   const float* dist_token;    /* [768] */
   const float* pos_emb;       /* [tokens][768], tokens = 2 + 12*((max_length-16)/10+1) */
@@ -131,15 +143,15 @@ typedef struct zk_model zk_model;
 int zk_model_create(const zk_ast_weights* w, zk_model** out);
 void zk_model_destroy(zk_model* m);
 int zk_model_num_tokens(const zk_model* m);
-/* bytes of caller-provided workspace zk_model_forward* needs for `batch` windows */
-size_t zk_model_workspace_bytes(const zk_model* m, int batch);
+/* bytes of caller-provided workspace zk_model_forward* needs for `batch` windows at `precision` */
+size_t zk_model_workspace_bytes(const zk_model* m, int batch, int precision);
 
-/* Contract path: d_features [batch][max_length][128] f32 (already normalised, what
- * ASTFeatureExtractor returns) -> d_logits [batch][num_labels] f32.  If d_hidden != NULL the
- * final residual stream [batch][tokens][768] f32 (before the last LayerNorm) is copied there
- * (test hook). */
-int zk_model_forward(zk_model* m, const float* d_features, int batch, void* d_workspace, size_t workspace_bytes,
-                     float* d_logits, float* d_hidden, zk_stream_t stream);
+/* Contract path: d_features [rows][max_length][128] f32 (already normalised, what ASTFeatureExtractor returns)
+ * -> d_logits [batch][num_labels] f32.  Window i of the batch reads feature row (d_row_index ? d_row_index[i] : i)
+ * (the re-check pass re-runs a few rows of a batch it has already seen).  If d_hidden != NULL the final residual
+ * stream [batch][tokens][768] f32 (before the last LayerNorm) is copied there (test hook). */
+int zk_model_forward(zk_model* m, const float* d_features, const int32_t* d_row_index, int batch, int precision,
+                     void* d_workspace, size_t workspace_bytes, float* d_logits, float* d_hidden, zk_stream_t stream);
 /* Fused path (ref:322-328 / refc:499-500 without materialising (batch,1024,128)): window i of the
  * batch reads rows [first_frame_i, first_frame_i + valid_frames) of the continuous fbank d_fbank
  * [m][128] (un-normalised), first_frame_i = (d_window_index ? d_window_index[i] : window_base + i)
@@ -147,7 +159,7 @@ int zk_model_forward(zk_model* m, const float* d_features, int batch, void* d_wo
  * applied while gathering. */
 int zk_model_forward_fbank(zk_model* m, const float* d_fbank, int64_t fbank_frames, const int32_t* d_window_index,
                            int window_base, int frames_per_hop, int valid_frames, float mean, float std, int batch,
-                           void* d_workspace, size_t workspace_bytes, float* d_logits, zk_stream_t stream);
+                           int precision, void* d_workspace, size_t workspace_bytes, float* d_logits, zk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (5) Stage-1 gate + order-preserving compaction -- replaces ref:111 (softmax) and ref:312-320
@@ -160,6 +172,15 @@ int zk_gate_compact(const float* d_logits, int n, float threshold, float min_pro
                     int32_t* d_index, int32_t* d_count, zk_stream_t stream);
 /* softmax only (Stage 2: ref:111) */
 int zk_softmax2(const float* d_logits, int n, float* d_probs, zk_stream_t stream);
+/* Decision re-check selection: rows i of d_logits [n][2] whose margin l1 - l0 lies within eps of ANY of the
+ * num_margins decision points h_margins[] (HOST array, <= 4 entries; logit(thr) of every threshold applied to the stage:
+ * ref:313-317 argmax (0) and p1 >= thr, refc:471-478 forward_min_prob, ref:333 / refc:512-520 p_zenker >= thr2).
+ * Order-preserving compaction: d_pos[j] = i (row to overwrite later), d_window[j] = d_src_window ? d_src_window[i] : i
+ * (window index to re-run), d_count[0] = how many.  Integer outputs are exact functions of d_logits. */
+int zk_band_select(const float* d_logits, int n, const float* h_margins, int num_margins, float eps,
+                   const int32_t* d_src_window, int32_t* d_pos, int32_t* d_window, int32_t* d_count, zk_stream_t stream);
+/* d_dst[d_pos[j]][0..1] = d_src[j][0..1] for j < count (logits of the re-checked windows back into place) */
+int zk_scatter_rows2(const float* d_src, const int32_t* d_pos, int count, float* d_dst, zk_stream_t stream);
 /* Dataset normalisation statistics (utils/compute_ast_normalization_stats.py:77-80): d_acc[0] += sum(x), d_acc[1] +=
  * sum(x^2) over n floats, accumulated in float64 (the caller zeroes d_acc before the first batch; zero-padded feature
  * rows simply add 0, so the continuous or the padded layout give the same sums). */
@@ -169,22 +190,42 @@ int zk_sum_sumsq_f64(const float* d_x, int64_t n, double* d_acc, zk_stream_t str
  * Building blocks, exported so the parity tests can pin each kernel separately.
  * ------------------------------------------------------------------------------------------ */
 enum zk_gemm_epilogue {
-  ZK_EPI_BIAS_BF16 = 0,      /* out bf16 [M][N] = acc + bias */
-  ZK_EPI_BIAS_GELU_BF16 = 1, /* out bf16 = gelu_erf(acc + bias)  (HF activations "gelu") */
-  ZK_EPI_BIAS_RESID_F32 = 2, /* out f32 [M][N] += acc + bias  (residual stream, in place) */
-  ZK_EPI_PATCH_F32 = 3       /* out f32 row (r/P)*(P+2)+2+r%P = acc + bias + pos[2 + r%P] (P = aux_rows) */
+  ZK_EPI_BIAS_BF16 = 0,      /* out 16-bit [M][N] = acc*s + bias (name kept from ABI 1; the format is operand_format) */
+  ZK_EPI_BIAS_GELU_BF16 = 1, /* out 16-bit = gelu_erf(acc*s + bias)  (HF activations "gelu") */
+  ZK_EPI_BIAS_RESID_F32 = 2, /* out f32 [M][N] += acc*s + bias  (residual stream, in place) */
+  ZK_EPI_PATCH_F32 = 3,      /* out f32 row (r/P)*(P+2)+2+r%P = acc*s + bias + pos[2 + r%P] (P = aux_rows) */
+  ZK_EPI_BIAS_SPLIT = 4,     /* out fp16 [M][2N]: hi plane at columns [0,N), lo plane at [N,2N), of acc*s + bias */
+  ZK_EPI_BIAS_GELU_SPLIT = 5 /* same of gelu_erf(acc*s + bias), erf from libdevice (no polynomial) */
 };
-/* C = A * W^T: d_a bf16 [M][K] row-major, d_w bf16 [N][K] row-major (nn.Linear layout), fp32
- * accumulation in TMEM.  N % 256 == 0, K % 64 == 0. d_aux: position table for ZK_EPI_PATCH_F32. */
+/* C = A * W^T, fp32 accumulation in TMEM.  N % 256 == 0, K % 64 == 0.
+ *   products == 1: d_a 16-bit [M][K] (row pitch lda elements, 0 = K), d_w 16-bit [N][K] (nn.Linear layout, pitch ldw)
+ *   products == 3: split operands, fp16 only: d_a [M][2K] = hi | lo planes, d_w [N][2K] = hi | lo planes;
+ *                  C = A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T
+ *   acc_scale: the accumulator is multiplied by it before the bias (weights pre-scaled by a power of two).
+ *   ldo: output row pitch in elements (0 = N, or 2N for the ..._SPLIT epilogues). d_aux: position table for PATCH. */
+int zk_gemm16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_out, int64_t ldo,
+              int64_t M, int N, int K, int epilogue, int operand_format, int products, float acc_scale,
+              const float* d_aux, int aux_rows, zk_stream_t stream);
+/* ABI-1 form: bf16 operands, one product, no scale */
 int zk_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int64_t M, int N, int K,
                  int epilogue, const float* d_aux, int aux_rows, zk_stream_t stream);
-/* rows of 768 f32 -> bf16, (x-mean)/sqrt(var+eps)*w+b with biased variance (HF:modeling...:260-261) */
+/* rows of 768 f32 -> 16-bit, (x-mean)/sqrt(var+eps)*w+b with biased variance (HF:modeling...:260-261);
+ * planes == 2 (fp16 only): d_out [rows][2*768] = hi | lo planes */
+int zk_layernorm16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows, int cols,
+                   int operand_format, int planes, zk_stream_t stream);
 int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows,
                       int cols, zk_stream_t stream);
-/* d_qkv bf16 [batch*tokens][2304] (q | k | v, head h at columns h*64) -> d_out bf16 [batch*tokens][768];
+/* d_qkv 16-bit [batch*tokens][2304] (q | k | v, head h at columns h*64) -> d_out 16-bit [batch*tokens][768];
  * softmax(q k^T / 8) v per (window, head), no mask (HF:modeling...:150-181). */
+int zk_attention16(const void* d_qkv, void* d_out, int batch, int tokens, int operand_format, zk_stream_t stream);
 int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream);
+/* Re-check precision: d_qkv fp16 [batch*tokens][2*2304] = hi | lo planes of (q | k | v) -> d_out fp16
+ * [batch*tokens][2*768] = hi | lo planes; scores and P V as three-product sums, softmax in fp32 with exp2f. */
+int zk_attention_split(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream);
 int zk_f32_to_bf16(const float* d_in, void* d_out, int64_t n, zk_stream_t stream);
+/* d_in f32 [rows][cols] * scale -> d_out [rows][planes*cols] 16-bit (planes == 2, fp16 only: hi | lo) */
+int zk_f32_to_16(const float* d_in, void* d_out, int64_t rows, int cols, int operand_format, int planes, float scale,
+                 zk_stream_t stream);
 /* zk_attention_bf16 + a device-clock timeline of the first 512 CTAs (128 int64 slots each; tuning aid, see
  * scripts/attn_trace.py for the slot layout). */
 int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, int64_t* d_trace, zk_stream_t stream);
@@ -197,7 +238,9 @@ int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, in
 enum zk_kernel_class {
   ZK_K_RESAMPLE = 0, ZK_K_FBANK = 1, ZK_K_GATHER = 2, ZK_K_GEMM_PATCH = 3, ZK_K_LAYERNORM = 4,
   ZK_K_GEMM_QKV = 5, ZK_K_ATTENTION = 6, ZK_K_GEMM_OUT = 7, ZK_K_GEMM_FC1 = 8, ZK_K_GEMM_FC2 = 9,
-  ZK_K_HEAD = 10, ZK_K_GATE = 11, ZK_K_MISC = 12, ZK_K_TAIL = 13, ZK_K_NUM_CLASSES = 14
+  ZK_K_HEAD = 10, ZK_K_GATE = 11, ZK_K_MISC = 12, ZK_K_TAIL = 13,
+  ZK_K_RECHECK = 14, /* every launch of a ZK_PRECISION_RECHECK forward */
+  ZK_K_NUM_CLASSES = 15
 };
 void zk_prof_enable(int time_launches);
 /* ms[ZK_K_NUM_CLASSES] (0 where timing was off), launches[ZK_K_NUM_CLASSES]; returns 0 or a cudaError_t */

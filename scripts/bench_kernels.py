@@ -30,23 +30,24 @@ def main():
     B = int(os.environ.get("ZK_BENCH_BATCH", "128"))
     T = 1214
     M = B * T
-    out = {}
+    DT = torch.bfloat16 if os.environ.get("ZK_OPERANDS", "fp16").lower().startswith("b") else torch.float16
+    out = {"operands": str(DT)}
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(M, 768, device="cuda", generator=g)
-    a768 = (torch.randn(M, 768, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
-    a3072 = (torch.randn(M, 3072, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    a768 = (torch.randn(M, 768, device="cuda", generator=g) * 0.5).to(DT)
+    a3072 = (torch.randn(M, 3072, device="cuda", generator=g) * 0.5).to(DT)
     for name, a, N, K, epi in (("gemm_qkv", a768, 2304, 768, _lib.EPI_BIAS_BF16), ("gemm_fc1", a768, 3072, 768, _lib.EPI_BIAS_GELU_BF16),
                                ("gemm_out", a768, 768, 768, _lib.EPI_BIAS_RESID_F32), ("gemm_fc2", a3072, 768, 3072, _lib.EPI_BIAS_RESID_F32)):
-        w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).to(DT)
         b = torch.randn(N, device="cuda", generator=g) * 0.1
-        o = x if epi == _lib.EPI_BIAS_RESID_F32 else torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        o = x if epi == _lib.EPI_BIAS_RESID_F32 else torch.empty(M, N, device="cuda", dtype=DT)
         ms = timeit(lambda: ops.gemm(a, w, b, epi, out=o))
         tf = 2.0 * M * N * K / ms / 1e9
         out[name] = {"ms": ms, "tflops": tf, "frac_burst": tf / PEAKS["bf16_tflops"], "frac_sustained": tf / PEAKS["bf16_tflops_sustained"]}
         ref = timeit(lambda: torch.matmul(a, w.t()))
         out[name]["cublas_ms"] = ref
         del w, o
-    qkv = (torch.randn(M, 2304, device="cuda", generator=g)).to(torch.bfloat16)
+    qkv = (torch.randn(M, 2304, device="cuda", generator=g)).to(DT)
     qkv[:, :1536] *= 2.0
     ms = timeit(lambda: ops.attention(qkv, B, T))
     tf = 4.0 * B * 12 * T * T * 64 / ms / 1e9
@@ -70,6 +71,25 @@ def main():
     ms = timeit(lambda: ops.layernorm(x, w, w, 1e-12))
     out["layernorm"] = {"ms": ms, "gbs": M * 768 * 6 / ms / 1e6, "frac_hbm": M * 768 * 6 / ms / 1e6 / PEAKS["hbm_gbs"]}
     del x, a768, a3072
+    # re-check precision (split operands, three products) at a re-check batch of 16 windows
+    Bs = int(os.environ.get("ZK_BENCH_RECHECK_BATCH", "16"))
+    Ms = Bs * T
+    xs = torch.randn(Ms, 768, device="cuda", generator=g)
+    for name, K, N, epi in (("split_qkv", 768, 2304, _lib.EPI_BIAS_SPLIT), ("split_fc1", 768, 3072, _lib.EPI_BIAS_GELU_SPLIT),
+                            ("split_out", 768, 768, _lib.EPI_BIAS_RESID_F32), ("split_fc2", 3072, 768, _lib.EPI_BIAS_RESID_F32)):
+        a2 = ops.split_f16(torch.randn(Ms, K, device="cuda", generator=g) * 0.5)
+        w2 = ops.split_f16(torch.randn(N, K, device="cuda", generator=g) * 0.02, 2.0 ** 17)
+        b = torch.randn(N, device="cuda", generator=g) * 0.1
+        o = xs if epi == _lib.EPI_BIAS_RESID_F32 else torch.empty(Ms, 2 * N, device="cuda", dtype=torch.float16)
+        ms = timeit(lambda: ops.gemm(a2, w2, b, epi, out=o, products=3, acc_scale=2.0 ** -17))
+        tf = 3 * 2.0 * Ms * N * K / ms / 1e9
+        out[name] = {"ms": ms, "tflops_executed": tf, "frac_sustained": tf / PEAKS["bf16_tflops_sustained"], "batch": Bs}
+        del a2, w2, o
+    q2 = ops.split_f16(torch.randn(Ms, 2304, device="cuda", generator=g) * 1.5)
+    ms = timeit(lambda: ops.attention_split(q2, Bs, T))
+    tf = 3 * 4.0 * Bs * 12 * T * T * 64 / ms / 1e9
+    out["split_attention"] = {"ms": ms, "tflops_executed": tf, "batch": Bs, "ms_per_window": ms / Bs}
+    del q2, xs
     # fbank cfg3: 1 h @ 16 kHz in one launch (algorithmic bytes 4 n + 512 m); repeat on 4 h to amortise launch overhead
     plan = ops.FbankPlan()
     for hours in (1, 4):

@@ -264,6 +264,45 @@ def gold_cascade_60s():
     print("cascade_60s", len(windows), len(idx), summ)
 
 
+def gold_cascade_cfg2():
+    """BASELINE.json configs[1] at FULL size: the 600-s 48 kHz recording the bench runs (synth.recording seed 2002) ->
+    1199 windows through ref.forward_probs (Stage 1 on all, Stage 2 on the forwarded ones), the reference gate and
+    ref.summarize_stage_outputs at thresholds 0.5 / 0.5 and at 0.6 / 0.35 (the counting quirk of SURVEY.md 0.7; its
+    forwarded set is a subset of the first run's, so no further forward is needed).  ~25 min on 8 cores.
+    The head biases are the ones derived for cascade_60s.npz."""
+    g = np.load(os.path.join(GOLD, "cascade_60s.npz"))
+    b1, b2 = float(g["head_bias1_s1"]), float(g["head_bias1_s2"])
+    fx1 = T.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
+    fx2 = T.hf_feature_extractor(synth.STAGE2_MEAN, synth.STAGE2_STD)
+    rec = synth.recording(600.0, 48000, seed=2002)
+    audio = T.resample(rec, 48000, 16000)
+    windows = ref.window_audio(audio, 1.0, 0.5)
+    m1 = T.hf_model_from_state_dict(synth.random_state_dict(11, head_bias1=b1))
+    m2 = T.hf_model_from_state_dict(synth.random_state_dict(22, head_bias1=b2))
+    s1 = ref.forward_probs(m1, fx1, windows, 16)
+    out = {}
+    s2_by_window = {}
+    for tag, thr1, thr2 in (("a", 0.5, 0.5), ("b", 0.6, 0.35)):
+        preds = s1.argmax(axis=1)
+        preds = np.where((preds == 1) & (s1[:, 1] >= thr1), 1, 0)   # ref:313-317
+        idx = np.where(preds == 1)[0]
+        todo = [i for i in idx if int(i) not in s2_by_window]
+        if todo:
+            p = ref.forward_probs(m2, fx2, [windows[i] for i in todo], 16)
+            for i, row in zip(todo, p):
+                s2_by_window[int(i)] = row
+        s2 = np.stack([s2_by_window[int(i)] for i in idx]) if len(idx) else np.zeros((0, 2), np.float32)
+        results = [(int(gi), s2[i]) for i, gi in enumerate(idx)]
+        summ = ref.summarize_stage_outputs(s1, results, ["Idle", "Swallow"], ["Healthy", "Zenker"], thr2)
+        out[f"swallow_indices_{tag}"] = idx
+        out[f"s2_probs_{tag}"] = s2
+        out[f"summary_{tag}"] = json.dumps(summ)
+        out[f"thresholds_{tag}"] = np.array([thr1, thr2])
+        print("cascade_cfg2", tag, len(windows), len(idx), summ)
+    np.savez_compressed(os.path.join(GOLD, "cascade_cfg2.npz"), s1_probs=s1, head_bias1_s1=b1, head_bias1_s2=b2,
+                        n_windows=len(windows), audio16k_head=audio[:64], **out)
+
+
 CACHE_FIXTURE_DIR = "/tmp/zk_cache_golden"  # absolute on purpose: the cache key hashes the absolute path (refc:97-100)
 
 
@@ -352,3 +391,5 @@ if __name__ == "__main__":
             gold_ast_plain()
         if "cascade60" in todo:
             gold_cascade_60s()
+        if "cascadecfg2" in todo:  # only on request (--only cascadecfg2): ~25 min of CPU
+            gold_cascade_cfg2()

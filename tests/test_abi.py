@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_pure_host_entry_points(lib):
-    assert lib.zk_abi_version() == 1
+    assert lib.zk_abi_version() == 2
     assert lib.zk_fbank_num_frames(16000) == 98
     assert lib.zk_fbank_num_frames(399) == 0 and lib.zk_fbank_num_frames(400) == 1
     assert lib.zk_fbank_num_frames(9_600_000) == 59998
@@ -48,7 +48,8 @@ def test_struct_layout_matches_header(lib):
     from zenker_audio_detection_b200 import _lib
 
     assert ctypes.sizeof(_lib.AstLayerWeights) == 16 * 8
-    assert ctypes.sizeof(_lib.AstWeights) == 16 + 5 * 8 + 12 * 16 * 8 + 6 * 8
+    assert ctypes.sizeof(_lib.AstWeights) == 16 + 8 + 5 * 8 + 12 * 16 * 8 + 6 * 8  # operand_format + padding
+    assert _lib.AstWeights.cls_token.offset == 24
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

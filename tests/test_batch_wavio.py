@@ -72,8 +72,9 @@ def test_wav_rejects_garbage(tmp_path):
 
 
 def _tree(tmp_path):
+    # ids are matched as SUBSTRINGS of the directory path (ref:123), so none of them may occur in pytest's tmp path (pytest-NN)
     root = tmp_path / "long"
-    lens = {"Healthy/224": [1600, 800, 2400], "Zenker/301": [1200, 900], "Zenker/17": [500]}
+    lens = {"Healthy/224": [1600, 800, 2400], "Zenker/301": [1200, 900], "Zenker/9017": [500]}
     for rel, ns in lens.items():
         d = root / rel
         d.mkdir(parents=True)
@@ -82,7 +83,7 @@ def _tree(tmp_path):
         (d / "notes.txt").write_text("x")
     ids = tmp_path / "ids"
     ids.mkdir()
-    (ids / "test_ids_fold3.txt").write_text("Healthy/224\n\nZenker/301\nZenker/17\n")
+    (ids / "test_ids_fold3.txt").write_text("Healthy/224\n\nZenker/301\nZenker/9017\n")
     return root, ids
 
 
@@ -92,13 +93,13 @@ def test_discover_two_files_follows_the_reference(tmp_path):
     assert [os.path.basename(p) for p in two] == ["rec0.wav", "rec1.wav"]  # sorted (ref:128)
     longest = batch.discover_two_files(str(root), "224", "*.wav")  # > 2 files: the two with most frames (ref:129-137)
     assert [os.path.basename(p) for p in longest] == ["rec2.wav", "rec0.wav"]
-    with pytest.raises(ValueError, match="Expected exactly 2 files for patient 17, found 1"):
-        batch.discover_two_files(str(root), "17", "*.wav")
+    with pytest.raises(ValueError, match="Expected exactly 2 files for patient 9017, found 1"):
+        batch.discover_two_files(str(root), "9017", "*.wav")
 
 
 def test_ids_thresholds_and_plan(tmp_path, capsys):
     root, ids = _tree(tmp_path)
-    assert batch.read_ids(str(ids / "test_ids_fold3.txt")) == ["224", "301", "17"]
+    assert batch.read_ids(str(ids / "test_ids_fold3.txt")) == ["224", "301", "9017"]
     cfg = {"folds": {"3": {"stage1": {"threshold": 0.61}, "stage2": {"threshold": 0.35}}},
            "thresholds": {"stage1": {"threshold": 0.9}}}
     assert batch.resolve_thresholds(cfg, 3) == (0.61, 0.35)       # per-fold block wins (ref batch:97-108)
@@ -113,7 +114,7 @@ def test_ids_thresholds_and_plan(tmp_path, capsys):
     assert sorted(pid for pl in plans for pid, _ in pl) == ["224"]  # 301 exists -> skipped, 17 has one file -> error
     assert batch.run(args, 0, 1) == 0
     printed = capsys.readouterr().out
-    assert "[SKIP] 301" in printed and "[ERROR] patient 17" in printed and "[RUN] rank 0: 224" in printed
+    assert "[SKIP] 301" in printed and "[ERROR] patient 9017" in printed and "[RUN] rank 0: 224" in printed
     args.force = True
     assert sorted(pid for pid, _ in batch.plan_patients(args, 0, 1)[0]) == ["224", "301"]
 

@@ -98,6 +98,53 @@ def test_cfg2_stage2_equals_direct_forward(cfg2):
     assert np.abs(probs - res.s2_probs[sel]).max() <= 2e-3  # same kernels; the fused path normalises on the fly
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_cfg2_decisions_equal_the_reference_run(golden_dir, tag):
+    """The headline configuration against the reference ITSELF: tests/golden/cascade_cfg2.npz holds what
+    ref.window_audio / ref.forward_probs / the reference gate / ref.summarize_stage_outputs produced on the CPU for this
+    very 600-s recording and these weights (scripts/make_golden.py::gold_cascade_cfg2, ~25 min of CPU), at thresholds
+    0.5 / 0.5 (a) and 0.6 / 0.35 (b, the counting quirk of SURVEY.md 0.7).  Every integer of the result must be equal:
+    the forwarded index list over all 1199 windows, the per-window classes, every count and ratio of the summary."""
+    import json
+    import os
+
+    from oracle import glue
+    from zenker_audio_detection_b200 import synth
+    from zenker_audio_detection_b200.fx import ZenkerASTFeatureExtractor
+    from zenker_audio_detection_b200.model import ZenkerASTForAudioClassification
+    from zenker_audio_detection_b200.pipeline import TwoStagePipeline
+
+    g = np.load(os.path.join(golden_dir, "cascade_cfg2.npz"))
+    thr1, thr2 = (float(v) for v in g[f"thresholds_{tag}"])
+    fx1 = ZenkerASTFeatureExtractor(mean=synth.STAGE1_MEAN, std=synth.STAGE1_STD)
+    fx2 = ZenkerASTFeatureExtractor(mean=synth.STAGE2_MEAN, std=synth.STAGE2_STD)
+    m1 = ZenkerASTForAudioClassification({"max_length": 1024}, synth.random_state_dict(11, head_bias1=float(g["head_bias1_s1"])))
+    m2 = ZenkerASTForAudioClassification({"max_length": 1024}, synth.random_state_dict(22, head_bias1=float(g["head_bias1_s2"])))
+    pipe = TwoStagePipeline(m1, fx1, m2, fx2, batch_size=128, stage1_threshold=thr1, stage2_threshold=thr2)
+    res = pipe.run_waveform(synth.recording(600.0, 48000, seed=2002), 48000)
+    assert res.num_windows == int(g["n_windows"]) == 1199
+    ref_idx, ref_s2 = g[f"swallow_indices_{tag}"], g[f"s2_probs_{tag}"]
+    p = g["s1_probs"].astype(np.float64)
+    margin = np.log(p[:, 1]) - np.log(p[:, 0])
+    print(f"cfg2[{tag}] thr {thr1}/{thr2}: re-checked {res.rechecked_s1} + {res.rechecked_s2} windows; forwarded ours/ref "
+          f"{len(res.swallow_indices)}/{len(ref_idx)}; max |p1 - ref| {np.abs(res.s1_probs - g['s1_probs']).max():.3g}; "
+          f"smallest reference |margin - decision point| "
+          f"{min(np.abs(margin - m).min() for m in pipe.margins1):.3g}")
+    assert np.array_equal(res.swallow_indices, ref_idx)
+    assert np.abs(res.s1_probs - g["s1_probs"]).max() <= 2.5e-3
+    assert np.abs(res.s2_probs - ref_s2).max() <= 2.5e-3
+    ref_classes = glue.stage2_classes(1199, [(int(i), q) for i, q in zip(ref_idx, ref_s2)], np.float32(thr2))
+    assert np.array_equal(res.classes, ref_classes)
+    ref_summary = json.loads(str(g[f"summary_{tag}"]))
+    for k, v in ref_summary.items():
+        if isinstance(v, (int, type(None))):
+            assert res.summary[k] == v, k
+        elif isinstance(v, float):
+            assert abs(res.summary[k] - v) <= 2.5e-3, k
+        else:
+            assert np.abs(np.asarray(res.summary[k]) - np.asarray(v)).max() <= 2.5e-3, k
+
+
 @pytest.fixture(scope="module")
 def cfg3():
     from zenker_audio_detection_b200 import ops
@@ -167,7 +214,7 @@ def test_cfg4_results_do_not_depend_on_order_or_rank():
 
 
 def test_cfg5_batch32_forward_is_batch_invariant_and_matches_the_fp32_oracle():
-    """cfg5: (32, 1024, 128) features ~ N(0, 0.5), seed 5005, 1214 tokens, bf16 weights.  The
+    """cfg5: (32, 1024, 128) features ~ N(0, 0.5), seed 5005, 1214 tokens, 16-bit weights.  The
     32-window forward equals four 8-window forwards and thirty-two single-window forwards bit for bit (tile shapes do
     not depend on the batch), and agrees with the fp32 oracle (HF's arithmetic restated, oracle/numerics.py) within the
     bf16 tolerance of north_star on a plain random init."""
@@ -186,4 +233,4 @@ def test_cfg5_batch32_forward_is_batch_invariant_and_matches_the_fp32_oracle():
     torch.backends.cuda.matmul.allow_tf32 = False
     with torch.inference_mode():
         ref = numerics.ast_forward({k: v.cuda() for k, v in sd.items()}, feats[:4])
-    assert (full[:4] - ref).abs().max().item() <= 1e-2
+    assert (full[:4] - ref).abs().max().item() <= 2e-3  # fp16 operands (1e-2 is north_star's bf16 bound)

@@ -20,6 +20,54 @@ def test_layernorm():
     assert torch.equal(out, ref.to(torch.bfloat16)) or (out.float() - ref.to(torch.bfloat16).float()).abs().max() <= 0.04
 
 
+def test_layernorm_fp16_and_planes():
+    from zenker_audio_detection_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1214 + 3, 768, device="cuda", generator=g) * 3 + 0.5
+    w = torch.randn(768, device="cuda", generator=g)
+    b = torch.randn(768, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (768,), w.double(), b.double(), 1e-12)
+    one = ops.layernorm(x, w, b, 1e-12, dtype=torch.float16)
+    assert one.dtype == torch.float16 and (one.double() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    two = ops.layernorm(x, w, b, 1e-12, dtype=torch.float16, planes=2)
+    assert two.shape == (x.shape[0], 1536)
+    assert torch.equal(two[:, :768], one)  # the hi plane IS the single-plane result
+    val = two[:, :768].double() + two[:, 768:].double()
+    assert (val - ref).abs().max().item() <= 4e-6 * ref.abs().max().item()  # fp32 LayerNorm arithmetic
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 1199, 5000])
+def test_band_select_and_scatter(n):
+    from zenker_audio_detection_b200 import ops
+
+    g = torch.Generator().manual_seed(n + 7)
+    logits = (torch.randn(n, 2, generator=g) * 0.2)
+    margins, eps = [0.0, 0.405], 0.03
+    d = (logits[:, 1] - logits[:, 0]).numpy()
+    if n > 3:
+        logits[2, 1] = float("nan")  # a NaN margin must be selected (never silently trusted)
+        d = (logits[:, 1] - logits[:, 0]).numpy()
+    want = np.where(~(np.minimum(np.abs(d - np.float32(0.0)), np.abs(d - np.float32(0.405))) > np.float32(eps)))[0]
+    src = torch.arange(n, dtype=torch.int32) * 3 + 1
+    dl = logits.cuda()
+    pos, window, count = ops.band_select(dl, margins, eps, src.cuda())
+    r = int(count.item())
+    assert r == len(want)
+    assert np.array_equal(pos[:r].cpu().numpy(), want.astype(np.int32))
+    assert np.array_equal(window[:r].cpu().numpy(), (want * 3 + 1).astype(np.int32))
+    pos2, window2, count2 = ops.band_select(dl, margins, eps)
+    assert int(count2.item()) == r and torch.equal(pos2[:r], window2[:r])
+    if r:
+        new = torch.arange(2 * r, dtype=torch.float32).view(r, 2).cuda() + 100
+        before = dl.clone()
+        ops.scatter_rows2(new, pos, r, dl)
+        keep = np.ones(n, bool)
+        keep[want] = False
+        assert torch.equal(dl[torch.from_numpy(want).cuda()], new)
+        assert torch.equal(dl[torch.from_numpy(np.where(keep)[0]).cuda()], before[torch.from_numpy(np.where(keep)[0]).cuda()])
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 1024, 1199, 7199, 50000])
 @pytest.mark.parametrize("thr,minp", [(0.5, None), (0.8, None), (0.5, 0.7), (0.3, None)])
 def test_gate_compact_bit_exact(n, thr, minp):

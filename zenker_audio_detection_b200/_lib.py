@@ -16,7 +16,10 @@ LIB_NAME = "libzk_b200.so"
 LIB_PATH = os.environ.get("ZK_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 AST_LAYERS = 12
 
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32 = 0, 1, 2, 3
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_BIAS_SPLIT, EPI_BIAS_GELU_SPLIT = 0, 1, 2, 3, 4, 5
+FMT_BF16, FMT_F16 = 0, 1                  # zk_operand_format
+PRECISION_FAST, PRECISION_RECHECK = 0, 1  # zk_precision
+ABI_VERSION = 2
 
 
 class ZkError(RuntimeError):
@@ -35,6 +38,7 @@ class AstLayerWeights(C.Structure):
 class AstWeights(C.Structure):
     _fields_ = [
         ("num_layers", C.c_int32), ("max_length", C.c_int32), ("num_labels", C.c_int32), ("ln_eps", C.c_float),
+        ("operand_format", C.c_int32),
         ("cls_token", C.c_void_p), ("dist_token", C.c_void_p), ("pos_emb", C.c_void_p),
         ("patch_w", C.c_void_p), ("patch_b", C.c_void_p),
         ("layer", AstLayerWeights * AST_LAYERS),
@@ -62,16 +66,26 @@ SIGNATURES = {
     "zk_model_create": (C.c_int, [C.POINTER(AstWeights), C.POINTER(C.c_void_p)]),
     "zk_model_destroy": (None, [C.c_void_p]),
     "zk_model_num_tokens": (C.c_int, [C.c_void_p]),
-    "zk_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
-    "zk_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
-                                   C.c_void_p]),
+    "zk_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "zk_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "zk_model_forward_fbank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                         C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                          C.c_void_p]),
     "zk_gate_compact": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "zk_softmax2": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "zk_band_select": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zk_scatter_rows2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "zk_sum_sumsq_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zk_gemm16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "zk_layernorm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]),
+    "zk_attention16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "zk_attention_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "zk_f32_to_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "zk_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p]),
     "zk_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int,
@@ -83,7 +97,7 @@ SIGNATURES = {
     "zk_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zk_kernel_class_name": (C.c_char_p, [C.c_int]),
 }
-NUM_KERNEL_CLASSES = 14
+NUM_KERNEL_CLASSES = 15
 
 
 def prof_enable(time_launches: bool) -> None:
@@ -115,8 +129,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.zk_abi_version() != 1:
-        raise ZkError(f"ABI version mismatch: library {lib.zk_abi_version()} != binding 1")
+    if lib.zk_abi_version() != ABI_VERSION:
+        raise ZkError(f"ABI version mismatch: library {lib.zk_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

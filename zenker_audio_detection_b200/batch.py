@@ -96,12 +96,23 @@ class WavPrefetcher:
             self._next += 1
 
     def get(self, path: str):
-        if self._pending is None or self._pending[0] != path:
-            return self._reader(path)  # out of order (or exhausted): read synchronously
-        fut = self._pending[1]
+        if self._pending is not None and self._pending[0] == path:
+            fut = self._pending[1]
+            try:
+                return fut.result()
+            finally:
+                self._submit()
+        # Out of order: a patient failed on its first file and the caller moved on, so the pending decode is for a file
+        # nobody will ask for.  Drop it (and the buffer it holds), read this one synchronously and re-arm the
+        # prefetch on whatever follows `path` in the plan, so that the remaining reads overlap again.
+        if self._pending is not None:
+            self._pending[1].cancel()
+            self._pending = None
         try:
-            return fut.result()
+            return self._reader(path)
         finally:
+            if path in self._paths:
+                self._next = self._paths.index(path) + 1
             self._submit()
 
     def close(self) -> None:
@@ -137,8 +148,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
     return ap
 
 
-def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str]]], List[str]]:
-    """-> (this rank's ``[(patient, [file_a, file_b])]``, log lines).  Every rank computes the same global plan."""
+def global_plan(args) -> Tuple[List[Tuple[str, List[str], int]], List[str]]:
+    """-> (``[(patient, [file_a, file_b], bytes)]`` still to do, log lines).  Depends on the file system (which result
+    files already exist), so under torchrun it is computed ONCE, on rank 0, and broadcast (``plan_patients``)."""
     ids_root = args.ids_root or os.path.join(os.getcwd(), "data_ast_stage2")
     ids_path = os.path.join(ids_root, f"test_ids_fold{args.fold}.txt")
     if not os.path.exists(ids_path):
@@ -155,12 +167,30 @@ def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str
         except ValueError as e:
             log.append(f"[ERROR] patient {pid}: {e}")  # ref batch:286-289: a failing patient does not stop the batch
             continue
-        todo.append((pid, files))
+        todo.append((pid, files, sum(os.path.getsize(p) for p in files)))
+    return todo, log
+
+
+def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str]]], List[str]]:
+    """-> (this rank's ``[(patient, [file_a, file_b])]``, log lines).
+
+    With more than one rank the plan is made by rank 0 alone and broadcast: a rank that started late would otherwise see
+    result files an early rank has already written, skip those patients, shard a DIFFERENT list and drop or duplicate
+    work.  The exchange goes over a gloo group (host objects); ranks then shard the identical list longest-first."""
     from .dist import shard_recordings
 
-    sizes = [sum(os.path.getsize(p) for p in files) for _, files in todo]
-    mine = shard_recordings(sizes, world)[rank] if todo else []
-    return [todo[i] for i in mine], log
+    if world > 1:
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+        box = [global_plan(args) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        todo, log = box[0]
+    else:
+        todo, log = global_plan(args)
+    mine = shard_recordings([b for _, _, b in todo], world)[rank] if todo else []
+    return [(todo[i][0], todo[i][1]) for i in mine], log
 
 
 def run(args, rank: int = 0, world: int = 1) -> int:

@@ -140,7 +140,9 @@ def window_audio(audio: Union[np.ndarray, torch.Tensor], window_sec: float, hop_
     return a.as_strided((n, win), (hop, 1))
 
 
-def _logits_from_features(model, features: torch.Tensor, batch_size: int, device: torch.device) -> torch.Tensor:
+def _logits_from_features(model, features: torch.Tensor, batch_size: int, device: torch.device,
+                          rechecked: Optional[list] = None) -> torch.Tensor:
+    """``model(batch).logits`` per batch (the drop-in ``__call__`` re-checks borderline windows itself, model.py)."""
     out = torch.empty((features.size(0), model.num_labels), dtype=torch.float32, device=device)
     with torch.inference_mode():
         for start in range(0, features.size(0), batch_size):
@@ -148,6 +150,8 @@ def _logits_from_features(model, features: torch.Tensor, batch_size: int, device
             if not batch.is_cuda:
                 batch = (batch if batch.is_pinned() else batch.pin_memory()).to(device, non_blocking=True)
             out[start:start + batch.size(0)] = model(batch).logits
+            if rechecked is not None:
+                rechecked[0] += int(getattr(model, "last_rechecked", 0))
     return out
 
 
@@ -165,7 +169,7 @@ def run_recording_cached(pipe: TwoStagePipeline, audio_path: str, windows, cache
     """One recording through the cached flow of refc:433-531 with ``pipe``'s models, extractors and thresholds.
 
     ``windows``: what ``window_audio`` returns for the recording (list of ``(win,)`` float32 arrays) or the same as an
-    ``(N, win)`` tensor.  The scores equal ``pipe.run_waveform`` up to the bf16 forward's batch invariance; the gate,
+    ``(N, win)`` tensor.  The scores equal ``pipe.run_waveform`` up to the 16-bit forward's batch invariance; the gate,
     compaction, classes and summary are the same integer code paths.
     """
     n = len(windows)
@@ -173,7 +177,8 @@ def run_recording_cached(pipe: TwoStagePipeline, audio_path: str, windows, cache
     with torch.cuda.device(pipe.device):
         feats1 = load_or_compute_features(audio_path, windows, pipe.fx1, pipe.window_sec, pipe.hop_sec, pipe.batch_size,
                                           cache_dir, disable_cache, refresh_cache, "stage1", log)
-        logits1 = _logits_from_features(pipe.m1, feats1, pipe.batch_size, pipe.device)
+        re1, re2 = [0], [0]
+        logits1 = _logits_from_features(pipe.m1, feats1, pipe.batch_size, pipe.device, re1)
         if logits1.dim() != 2 or logits1.shape[1] != 2:
             raise RuntimeError("Stage1 output shape unexpected; expected (N,2)")  # refc:457-458
         probs1, pred, index, count = ops.gate_compact(logits1, pipe.thr1, pipe.min_prob)  # refc:459-475
@@ -184,7 +189,7 @@ def run_recording_cached(pipe: TwoStagePipeline, audio_path: str, windows, cache
                 audio_path, windows, pipe.fx2, pipe.window_sec, pipe.hop_sec, pipe.batch_size, cache_dir, disable_cache,
                 refresh_cache, "stage2", log)
             picked = feats2.index_select(0, torch.as_tensor(idx, dtype=torch.long, device=feats2.device))  # refc:497-498
-            logits2 = _logits_from_features(pipe.m2, picked, pipe.batch_size, pipe.device)
+            logits2 = _logits_from_features(pipe.m2, picked, pipe.batch_size, pipe.device, re2)
             if logits2.shape[1] != 2:
                 raise RuntimeError("Stage2 output shape unexpected; expected (K,2)")  # refc:502-503
             s2 = ops.softmax2(logits2).cpu().numpy()
@@ -194,4 +199,4 @@ def run_recording_cached(pipe: TwoStagePipeline, audio_path: str, windows, cache
         s1_preds = pred.cpu().numpy().astype(np.int64)
     classes = cascade.stage2_classes(n, idx, s2, pipe.thr2, pipe.stage2_argmax)
     summary = cascade.summarize_stage_outputs(s1, idx, s2, pipe.thr2, pipe.stage2_argmax)
-    return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary)
+    return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary, re1[0], re2[0])

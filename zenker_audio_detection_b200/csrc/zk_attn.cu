@@ -40,10 +40,11 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int THREADS = 384;  // warps 0-3: producer, MMA A, MMA B, spare; 4-7: softmax A; 8-11: softmax B
 // TMEM columns: S_t at 128 t (fp32), O_t at 256 + 64 t (fp32), P_t at 384 + 64 t (bf16 pairs, 128 keys)
 constexpr uint32_t TMEM_COLS = 512, TM_S = 0, TM_O = 256, TM_P = 384;
-constexpr float RESCALE_TAU = 24.0f;  // log2 units: p <= 2^24 against a stale maximum (fp32 sums / bf16 P keep their
-                                     // relative precision; 1214 keys * 2^24 * |v| is nowhere near fp32 range)
-constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, 0, 0);
-constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V) is MN-major
+// log2 units: p <= 2^tau against a stale maximum.  bf16 P keeps its relative precision over the whole fp32 exponent
+// range (tau 24: 1214 keys * 2^24 * |v| is nowhere near fp32 range); fp16 P must stay below 65504 (tau 15), and its
+// values below 2^-14 relative to a row sum >= 1 are subnormal, i.e. still good to 2^-25 of the sum.
+template <int FMT>
+constexpr float rescale_tau() { return FMT == FMT_F16 ? 15.0f : 24.0f; }
 constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
 constexpr int REGS_SOFTMAX = 216, REGS_OTHER = 56;
 static_assert(128 * REGS_OTHER + 256 * REGS_SOFTMAX <= 65536, "register file");
@@ -121,7 +122,7 @@ struct SoftmaxState {
 //
 // W = how many key columns of the block are processed at all: a ragged last block with kmax <= 64 valid keys (tokens =
 // 1214 leaves 62) only takes the lower half of S, writes the lower half of P, and the issuer shortens P V to W keys.
-template <bool RAGGED, bool FIRST, int POLY, int W = 128>
+template <bool RAGGED, bool FIRST, int POLY, int FMT, int W = 128>
 __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_valid, uint32_t t_s, uint32_t t_o, uint32_t t_p,
                                               uint64_t* s_free, uint64_t* pv_done, SoftmaxState& st, long long* trj) {
   uint32_t s[128];
@@ -177,8 +178,8 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
         const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
         lba = fadd2(lba, pa);
         lbb = fadd2(lbb, pb);
-        pk[i >> 1] = pack_bf16(pa.x, pa.y);
-        pk[(i >> 1) + 1] = pack_bf16(pb.x, pb.y);
+        pk[i >> 1] = pack16<FMT>(pa.x, pa.y);
+        pk[(i >> 1) + 1] = pack16<FMT>(pb.x, pb.y);
         if (!FIRST) {
           if (i & 4) {
             mx2 = fmax3(mx2, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
@@ -200,7 +201,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
     // Only rows that are real queries of this window vote, and only rows that exceed the threshold themselves move
     // their maximum: a row's result must not depend on what else shares its warp (the rows past the last token of a
     // window hold the NEXT window's queries, i.e. they change with the batch composition).
-    const bool exceed = row_valid && (mx - st.m) * SCALE_LOG2E > RESCALE_TAU;
+    const bool exceed = row_valid && (mx - st.m) * SCALE_LOG2E > rescale_tau<FMT>();
     if (!__any_sync(0xffffffffu, exceed)) break;
     // rare: advance the running maximum, rescale the accumulator in TMEM (whole warp, tcgen05 is collective), redo
     const float mn = exceed ? mx : st.m;
@@ -222,10 +223,12 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
   tmem_st_wait();
 }
 
-template <int POLY>
+template <int POLY, int FMT>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int tokens,
             int num_items, int qpairs, int stagger, int half_keys, long long* trace, int trace_items) {
+  constexpr uint32_t IDESC_S = umma_idesc_16(FMT, BQ, BKV, 0, 0);
+  constexpr uint32_t IDESC_O = umma_idesc_16(FMT, BQ, D, 0, 1);  // B (= V) is MN-major
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;          // [2] item parity
@@ -399,19 +402,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
         if (kmax <= half_keys) {
           if (j == 0)
-            softmax_block<true, true, POLY, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, true, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
-            softmax_block<true, false, POLY, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, false, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         } else if (kmax < BKV) {
           if (j == 0)
-            softmax_block<true, true, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
-            softmax_block<true, false, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         } else {
           if (j == 0)
-            softmax_block<false, true, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
           else
-            softmax_block<false, false, POLY>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
         }
         tc_fence_before();
         mbar_arrive(&p_full[t]);
@@ -436,10 +439,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         st_shared_v4(stg_row + ((uint32_t)(g ^ (row & 7)) << 4),
-                     pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv),
-                     pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv),
-                     pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv),
-                     pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv));
+                     pack16<FMT>(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv),
+                     pack16<FMT>(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv),
+                     pack16<FMT>(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv),
+                     pack16<FMT>(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv));
       fence_proxy_async();
       named_bar_sync(1 + t, 128);
       if (leader) {
@@ -459,18 +462,35 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
 }  // namespace attn
 
-int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long long* trace, cudaStream_t stream) {
+template <int POLY, int FMT>
+static int launch_attn(const CUtensorMap& tm, const CUtensorMap& o, int grid, int tokens, int items, int qpairs, int stagger,
+                       int half_keys, long long* trace, int trace_items, cudaStream_t stream) {
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn::attn_kernel<POLY, FMT>), attn::SMEM_BYTES, &attr_done))
+    return rc;
+  ProfScope prof(ZK_K_ATTENTION, stream);
+  attn::attn_kernel<POLY, FMT><<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, o, tokens, items, qpairs, stagger,
+                                                                               half_keys, trace, trace_items);
+  ZK_LAUNCH_CHECK("attn_kernel");
+  return 0;
+}
+
+int attention16_impl(const void* qkv, void* out, int batch, int tokens, int fmt, long long* trace, cudaStream_t stream) {
   using namespace attn;
   int rc = device_check();
   if (rc) return rc;
   if (!qkv || !out || batch <= 0 || tokens <= 0) {
-    set_error("attention_bf16: null pointer or empty shape");
+    set_error("attention16: null pointer or empty shape");
+    return ZK_ERR_ARG;
+  }
+  if (fmt != FMT_F16 && fmt != FMT_BF16) {
+    set_error("attention16: unknown operand format %d", fmt);
     return ZK_ERR_ARG;
   }
   const int qpairs = (tokens + QTILES * BQ - 1) / (QTILES * BQ);
   const long long items = (long long)qpairs * HEADS * batch;
   if (items > 0x7fffffffLL || (long long)batch * tokens > 0x7fffffffLL) {
-    set_error("attention_bf16: batch %d x tokens %d is too large", batch, tokens);
+    set_error("attention16: batch %d x tokens %d is too large", batch, tokens);
     return ZK_ERR_SHAPE;
   }
   // share of exp2 evaluated on the FMA pipe: 0, 1 or 2 of every 4 pairs (ZK_ATTN_POLY), start offset of tile B
@@ -486,36 +506,36 @@ int attention_bf16_impl(const void* qkv, void* out, int batch, int tokens, long 
   }();
   static const int half_keys = (getenv("ZK_ATTN_HALF") && atoi(getenv("ZK_ATTN_HALF")) == 0) ? 0 : BKV / 2;
   static const int trace_items = getenv("ZK_ATTN_TRACE_ITEMS") ? atoi(getenv("ZK_ATTN_TRACE_ITEMS")) : 0;
-  static unsigned long long attr_done[3] = {0, 0, 0};
-  const void* kernels[3] = {reinterpret_cast<const void*>(attn_kernel<0>), reinterpret_cast<const void*>(attn_kernel<1>),
-                            reinterpret_cast<const void*>(attn_kernel<2>)};
-  if ((rc = ensure_dynamic_smem(kernels[poly], SMEM_BYTES, &attr_done[poly]))) return rc;
   CUtensorMap tm;
   if ((rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * tokens, 3 * HID, 3 * HID, 128, 64))) return rc;
   const int grid = items < num_sms() ? (int)items : num_sms();
   CUtensorMap o;
   if ((rc = make_tmap_bf16_3d(&o, out, (uint64_t)batch, (uint64_t)tokens, HID, HID, (uint64_t)tokens * HID, 128, 64))) return rc;
-  ProfScope prof(ZK_K_ATTENTION, stream);
-  if (poly == 0)
-    attn_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
-  else if (poly == 1)
-    attn_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
-  else
-    attn_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, o, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items);
-  ZK_LAUNCH_CHECK("attn_kernel");
-  return 0;
+  const bool f16 = fmt == FMT_F16;
+#define ZK_ATTN_LAUNCH(P)                                                                                                     \
+  return f16 ? launch_attn<P, FMT_F16>(tm, o, grid, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items, stream) \
+             : launch_attn<P, FMT_BF16>(tm, o, grid, tokens, (int)items, qpairs, stagger, half_keys, trace, trace_items, stream)
+  if (poly == 0) { ZK_ATTN_LAUNCH(0); }
+  if (poly == 2) { ZK_ATTN_LAUNCH(2); }
+  ZK_ATTN_LAUNCH(1);
+#undef ZK_ATTN_LAUNCH
 }
 
-int attention_bf16(const void* qkv, void* out, int batch, int tokens, cudaStream_t stream) {
-  return attention_bf16_impl(qkv, out, batch, tokens, nullptr, stream);
+int attention16(const void* qkv, void* out, int batch, int tokens, int fmt, cudaStream_t stream) {
+  return attention16_impl(qkv, out, batch, tokens, fmt, nullptr, stream);
 }
 
 }  // namespace zk
 
 extern "C" int zk_attention_trace(const void* d_qkv, void* d_out, int batch, int tokens, int64_t* d_trace, zk_stream_t stream) {
-  return zk::attention_bf16_impl(d_qkv, d_out, batch, tokens, reinterpret_cast<long long*>(d_trace), (cudaStream_t)stream);
+  return zk::attention16_impl(d_qkv, d_out, batch, tokens, ZK_FMT_BF16, reinterpret_cast<long long*>(d_trace),
+                              (cudaStream_t)stream);
+}
+
+extern "C" int zk_attention16(const void* d_qkv, void* d_out, int batch, int tokens, int operand_format, zk_stream_t stream) {
+  return zk::attention16(d_qkv, d_out, batch, tokens, operand_format, (cudaStream_t)stream);
 }
 
 extern "C" int zk_attention_bf16(const void* d_qkv, void* d_out, int batch, int tokens, zk_stream_t stream) {
-  return zk::attention_bf16(d_qkv, d_out, batch, tokens, (cudaStream_t)stream);
+  return zk::attention16(d_qkv, d_out, batch, tokens, ZK_FMT_BF16, (cudaStream_t)stream);
 }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +40,35 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// fp16 pair, round to nearest even; values beyond +-65504 saturate instead of becoming inf (an inf operand would turn
+// a whole accumulator row into NaN)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit MMA operand formats (zk_operand_format of the C ABI): the tensor core runs both at the same rate
+// (tcgen05 kind::f16); fp16 keeps 11 significant bits against bf16's 8.
+constexpr int FMT_BF16 = 0, FMT_F16 = 1;
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  if constexpr (FMT == FMT_F16) return pack_f16(lo, hi);
+  else return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ uint32_t pack16_rt(int fmt, float lo, float hi) {  // format known at run time only
+  return fmt == FMT_F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+// (lo, hi) of a packed pair as fp32
+__device__ __forceinline__ float2 unpack16_rt(int fmt, uint32_t w) {
+  if (fmt == FMT_F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// x = hi + lo with hi, lo in fp16: 22 significant bits for |x| >= 2^-3, an absolute error below 2^-25 otherwise
+__device__ __forceinline__ void split_f16_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(x, y);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(x - h.x, y - h.y);
 }
 
 // ----------------------------------------------------------------------------- mbarrier
@@ -227,6 +257,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Same for either 16-bit operand format (a/b format fields: 0 = f16, 1 = bf16; accumulator f32).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int fmt, int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((fmt == FMT_F16 ? 0u : 1u) << 7) | ((fmt == FMT_F16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------- small device helpers

@@ -695,6 +695,14 @@ int zk_fbank_f32(const zk_fbank_plan* plan, const float* d_wave, int64_t n, floa
     zk::set_error("zk_fbank_f32: bad arguments");
     return ZK_ERR_ARG;
   }
+  {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != plan->device) {  // the tables live on the device the plan was created on
+      zk::set_error("%s: the plan belongs to device %d but the current device is %d", "zk_fbank_f32", plan->device, cur);
+      return ZK_ERR_ARG;
+    }
+  }
   if (m > zk_fbank_num_frames(n)) {
     zk::set_error("zk_fbank_f32: m = %lld frames requested but %lld samples hold only %lld", (long long)m, (long long)n,
                   (long long)zk_fbank_num_frames(n));
@@ -726,6 +734,14 @@ int zk_fx_contract_f32(const zk_fbank_plan* plan, const float* d_windows, int ba
   if (!plan || batch < 0 || win_len < 0 || win_pitch < win_len || max_length <= 0 || (batch > 0 && (!d_windows || !d_out))) {
     zk::set_error("zk_fx_contract_f32: bad arguments");
     return ZK_ERR_ARG;
+  }
+  {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != plan->device) {  // the tables live on the device the plan was created on
+      zk::set_error("%s: the plan belongs to device %d but the current device is %d", "zk_fx_contract_f32", plan->device, cur);
+      return ZK_ERR_ARG;
+    }
   }
   if (batch == 0) return 0;
   const int64_t m = zk_fbank_num_frames(win_len);

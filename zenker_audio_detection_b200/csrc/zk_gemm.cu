@@ -1,5 +1,13 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulation in
+// Persistent warp-specialised 16-bit GEMM for sm_100a: C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulation in
 // TMEM, operands staged by TMA into 128B-swizzled shared memory, tcgen05.mma issued by one thread.
+// Operands are fp16 or bf16 (template FMT; tcgen05 kind::f16 runs both at the same rate).
+//
+// Split-operand ("x2") mode for the decision re-check path: A and W are given as TWO fp16 planes each (x = hi + lo,
+// plane p at columns [p K, (p+1) K) of the row) and the kernel accumulates the three products A_lo W_hi + A_hi W_lo +
+// A_hi W_hi into the same TMEM accumulator -- the k-loop simply runs over 3 K/64 k-blocks whose TMA coordinates come
+// from a product table -- which carries 22 significant bits per operand (fp32-class results) at 3x the tensor time.
+// Weights are pre-scaled by a power of two (acc_scale undoes it exactly) so that their lo plane stays in fp16's
+// normal range.  The ..._SPLIT epilogues write their 16-bit output as hi / lo planes again.
 //
 //   warp 0      TMA producer   (4-stage ring of {A 128x64, W 256x64} bf16 tiles, 48 KiB / stage)
 //   warp 1      TMEM allocator + MMA issuer (UMMA 128x256x16, 4 per stage)
@@ -27,7 +35,7 @@ constexpr int STG_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 128 B (64 b
 constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+constexpr int MAX_PRODUCTS = 3;
 
 struct Params {
   const float* bias;
@@ -36,6 +44,11 @@ struct Params {
   long long M;
   int N, K, aux_rows;
   int num_m_tiles, num_n_tiles;
+  float acc_scale;             // result = acc * acc_scale + bias (undoes the power-of-two weight scale)
+  int nprod;                   // 1, or 3 in split-operand mode
+  int a_off[MAX_PRODUCTS];     // column (element) offset of the A plane of product i
+  int w_off[MAX_PRODUCTS];     // same for W
+  int out_plane_stride;        // ..._SPLIT epilogues: columns between the hi and lo output planes (= N)
 };
 
 // PATCH epilogue only: one thread owns 32 consecutive columns [col0, col0+32) of row `row`; rows are scattered to
@@ -52,10 +65,10 @@ __device__ __forceinline__ void patch_store(const Params& p, long long row, int 
   for (int i = 0; i < 8; ++i) {
     const float4 b = __ldg(bias4 + i);
     float4 o = __ldg(pos4 + i);
-    o.x += __uint_as_float(r[i * 4 + 0]) + b.x;
-    o.y += __uint_as_float(r[i * 4 + 1]) + b.y;
-    o.z += __uint_as_float(r[i * 4 + 2]) + b.z;
-    o.w += __uint_as_float(r[i * 4 + 3]) + b.w;
+    o.x += fmaf(__uint_as_float(r[i * 4 + 0]), p.acc_scale, b.x);
+    o.y += fmaf(__uint_as_float(r[i * 4 + 1]), p.acc_scale, b.y);
+    o.z += fmaf(__uint_as_float(r[i * 4 + 2]), p.acc_scale, b.z);
+    o.w += fmaf(__uint_as_float(r[i * 4 + 3]), p.acc_scale, b.w);
     dst[i] = o;
   }
 }
@@ -80,28 +93,150 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return make_float2(fmaf(-fabsf(x.x), fast_exp2(p.x), fmaxf(x.x, 0.f)), fmaf(-fabsf(x.y), fast_exp2(p.y), fmaxf(x.y, 0.f)));
 }
 
-// 32 accumulator columns (+bias, optional GELU) -> 16 packed bf16 pairs
-template <bool GELU>
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&r)[32], const float* bias, uint32_t (&pk)[16]) {
+// 32 accumulator columns (* scale + bias, optional GELU) -> 16 packed 16-bit pairs
+template <bool GELU, int FMT>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&r)[32], const float* bias, float scale, uint32_t (&pk)[16]) {
   const float4* bias4 = reinterpret_cast<const float4*>(bias);
+  const float2 sc2 = make_float2(scale, scale);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 b = __ldg(bias4 + i);
-    float2 v01 = fadd2(make_float2(__uint_as_float(r[i * 4 + 0]), __uint_as_float(r[i * 4 + 1])), make_float2(b.x, b.y));
-    float2 v23 = fadd2(make_float2(__uint_as_float(r[i * 4 + 2]), __uint_as_float(r[i * 4 + 3])), make_float2(b.z, b.w));
+    float2 v01 = ffma2(make_float2(__uint_as_float(r[i * 4 + 0]), __uint_as_float(r[i * 4 + 1])), sc2, make_float2(b.x, b.y));
+    float2 v23 = ffma2(make_float2(__uint_as_float(r[i * 4 + 2]), __uint_as_float(r[i * 4 + 3])), sc2, make_float2(b.z, b.w));
     if (GELU) {
       v01 = gelu_erf2(v01);
       v23 = gelu_erf2(v23);
     }
-    pk[i * 2 + 0] = pack_bf16(v01.x, v01.y);
-    pk[i * 2 + 1] = pack_bf16(v23.x, v23.y);
+    pk[i * 2 + 0] = pack16<FMT>(v01.x, v01.y);
+    pk[i * 2 + 1] = pack16<FMT>(v23.x, v23.y);
   }
 }
 
-template <int EPI>
+// erf-GELU as the reference evaluates it (HF activations "gelu" = torch.nn.functional.gelu, erf form), libdevice erff
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// split-operand epilogues: 32 accumulator columns (* scale + bias, optional exact GELU) -> fp16 hi and lo planes
+template <bool GELU>
+__device__ __forceinline__ void bias_act_split(const uint32_t (&r)[32], const float* bias, float scale, uint32_t (&hi)[16],
+                                               uint32_t (&lo)[16]) {
+  const float4* bias4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(bias4 + i);
+    float v0 = fmaf(__uint_as_float(r[i * 4 + 0]), scale, b.x), v1 = fmaf(__uint_as_float(r[i * 4 + 1]), scale, b.y);
+    float v2 = fmaf(__uint_as_float(r[i * 4 + 2]), scale, b.z), v3 = fmaf(__uint_as_float(r[i * 4 + 3]), scale, b.w);
+    if (GELU) {
+      v0 = gelu_exact(v0);
+      v1 = gelu_exact(v1);
+      v2 = gelu_exact(v2);
+      v3 = gelu_exact(v3);
+    }
+    split_f16_pair(v0, v1, hi[i * 2 + 0], lo[i * 2 + 0]);
+    split_f16_pair(v2, v3, hi[i * 2 + 1], lo[i * 2 + 1]);
+  }
+}
+
+constexpr bool epi_is_split(int epi) { return epi == ZK_EPI_BIAS_SPLIT || epi == ZK_EPI_BIAS_GELU_SPLIT; }
+
+// Epilogue of one accumulator tile for one warp (32 rows x 128 columns at t_acc), shared by the single-CTA and the
+// CTA-pair kernels: TMEM -> registers -> fused scale / bias / GELU -> 128B-swizzled staging tile -> TMA store (16-bit
+// outputs, one or two planes) or TMA reduce-add into the fp32 residual stream.
+template <int EPI, int FMT>
+__device__ __forceinline__ void epilogue_rows(const Params& p, const CUtensorMap* tmC, uint8_t* stg, uint32_t stg_row,
+                                              uint32_t t_acc, int row0, int col_base, int lane) {
+  if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
+    // 4 chunks of 32 fp32 columns: (acc * scale + bias) -> staging -> TMA reduce-add into the residual stream
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(t_acc + c * 32, r);
+      tmem_ld_wait();
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+      if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(bias4 + i);
+        st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4),
+                     __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 0]), p.acc_scale, b.x)),
+                     __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 1]), p.acc_scale, b.y)),
+                     __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 2]), p.acc_scale, b.z)),
+                     __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 3]), p.acc_scale, b.w)));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tmC, stg, col_base + c * 32, row0);
+        bulk_commit();
+      }
+    }
+  } else if constexpr (epi_is_split(EPI)) {
+    // 2 chunks of 64 columns, each stored twice: hi plane at column c, lo plane at column out_plane_stride + c
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_acc + c * 64, r0);
+      tmem_ld32(t_acc + c * 64 + 32, r1);
+      tmem_ld_wait();
+      uint32_t hi[32], lo[32];
+      bias_act_split<EPI == ZK_EPI_BIAS_GELU_SPLIT>(r0, p.bias + col_base + c * 64, p.acc_scale,
+                                                    *reinterpret_cast<uint32_t(*)[16]>(&hi[0]),
+                                                    *reinterpret_cast<uint32_t(*)[16]>(&lo[0]));
+      bias_act_split<EPI == ZK_EPI_BIAS_GELU_SPLIT>(r1, p.bias + col_base + c * 64 + 32, p.acc_scale,
+                                                    *reinterpret_cast<uint32_t(*)[16]>(&hi[16]),
+                                                    *reinterpret_cast<uint32_t(*)[16]>(&lo[16]));
+#pragma unroll
+      for (int plane = 0; plane < 2; ++plane) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (plane == 0)
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), hi[i * 4 + 0], hi[i * 4 + 1], hi[i * 4 + 2], hi[i * 4 + 3]);
+          else
+            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), lo[i * 4 + 0], lo[i * 4 + 1], lo[i * 4 + 2], lo[i * 4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, stg, plane * p.out_plane_stride + col_base + c * 64, row0);
+          bulk_commit();
+        }
+      }
+    }
+  } else {
+    // 2 chunks of 64 16-bit columns: (acc * scale + bias [, GELU]) -> staging -> TMA store
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_acc + c * 64, r0);
+      tmem_ld32(t_acc + c * 64 + 32, r1);
+      tmem_ld_wait();
+      uint32_t pk[32];
+      bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16, FMT>(r0, p.bias + col_base + c * 64, p.acc_scale,
+                                                       *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16, FMT>(r1, p.bias + col_base + c * 64 + 32, p.acc_scale,
+                                                       *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), pk[i * 4 + 0], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, stg, col_base + c * 64, row0);
+        bulk_commit();
+      }
+    }
+  }
+}
+
+template <int EPI, int FMT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const Params p) {
+  constexpr uint32_t IDESC = umma_idesc_16(FMT, BM, BN, 0, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -135,6 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.K / BK;
+  const int kblocks_all = kblocks * p.nprod;  // k-blocks the MMA warp consumes per tile (all products)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -142,15 +278,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+        for (int pr = 0; pr < p.nprod; ++pr) {
+          const int a0 = p.a_off[pr], w0 = p.w_off[pr];
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            tma_load_2d(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * BM);
+            tma_load_2d(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -167,7 +306,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < kblocks_all; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -179,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+          if (kb == kblocks_all - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -229,10 +368,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float4 b = __ldg(bias4 + i);
             const float4 o = __ldg(pos4 + i);
             st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x + o.x),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y + o.y),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z + o.z),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w + o.w));
+                         __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 0]), p.acc_scale, b.x) + o.x),
+                         __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 1]), p.acc_scale, b.y) + o.y),
+                         __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 2]), p.acc_scale, b.z) + o.z),
+                         __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 3]), p.acc_scale, b.w) + o.w));
           }
           fence_proxy_async();
           __syncwarp();
@@ -241,57 +380,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             bulk_commit();
           }
         }
-      } else if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
-        // 4 chunks of 32 fp32 columns: (acc + bias) -> staging -> TMA reduce-add into the residual stream
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_acc + c * 32, r);
-          tmem_ld_wait();
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
-          if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(bias4 + i);
-            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_reduce_add_2d(&tmC, stg, col_base + c * 32, row0);
-            bulk_commit();
-          }
-        }
       } else {
-        // 2 chunks of 64 bf16 columns: (acc + bias [, GELU]) -> staging -> TMA store
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_acc + c * 64, r0);
-          tmem_ld32(t_acc + c * 64 + 32, r1);
-          tmem_ld_wait();
-          uint32_t pk[32];
-          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r0, p.bias + col_base + c * 64,
-                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r1, p.bias + col_base + c * 64 + 32,
-                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), pk[i * 4 + 0], pk[i * 4 + 1], pk[i * 4 + 2],
-                         pk[i * 4 + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stg, col_base + c * 64, row0);
-            bulk_commit();
-          }
-        }
+        epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -320,7 +410,6 @@ constexpr int HALF_B_BYTES = 128 * BK * 2, STAGE2_BYTES = A_BYTES + HALF_B_BYTES
 constexpr int OFF_STG2 = STAGES2 * STAGE2_BYTES, OFF_BAR2 = OFF_STG2 + EPI_WARPS * STG_BYTES;
 constexpr int SMEM2_BYTES = OFF_BAR2 + 256 + 1024;
 static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget");
-constexpr uint32_t IDESC2 = umma_idesc_bf16(2 * BM, BN, 0, 0);
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address -> even CTA
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -372,11 +461,12 @@ __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
       : "memory");
 }
 
-template <int EPI>
+template <int EPI, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
   static_assert(EPI != ZK_EPI_PATCH_F32, "the patch-embedding epilogue stays on the single-CTA kernel");
+  constexpr uint32_t IDESC2 = umma_idesc_16(FMT, 2 * BM, BN, 0, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);  // leader's copy is the live one
@@ -413,6 +503,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row tiles here
   const int kblocks = p.K / BK;
+  const int kblocks_all = kblocks * p.nprod;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -421,15 +512,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);  // both CTAs' tiles land on this barrier
-          uint8_t* sa = smem + stage * STAGE2_BYTES;
-          tma_load_2d_pair(sa, &tmA, &full[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
-          tma_load_2d_pair(sa + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN + (int)rank * 128);
-          if (++stage == STAGES2) {
-            stage = 0;
-            phase ^= 1;
+        for (int pr = 0; pr < p.nprod; ++pr) {
+          const int a0 = p.a_off[pr], w0 = p.w_off[pr];
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);  // both CTAs' tiles land on this barrier
+            uint8_t* sa = smem + stage * STAGE2_BYTES;
+            tma_load_2d_pair(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * 2 * BM + (int)rank * BM);
+            tma_load_2d_pair(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN + (int)rank * 128);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -445,7 +539,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks_all; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -455,7 +549,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC2, (kb | k) != 0);
             umma_commit_pair(&empty[stage]);
-            if (kb == kblocks - 1) umma_commit_pair(&tfull[acc]);
+            if (kb == kblocks_all - 1) umma_commit_pair(&tfull[acc]);
           }
           __syncwarp();
           if (++stage == STAGES2) {
@@ -480,56 +574,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
       const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
-      if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_acc + c * 32, r);
-          tmem_ld_wait();
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(bias4 + i);
-            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[i * 4 + 0]) + b.x),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 1]) + b.y),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 2]) + b.z),
-                         __float_as_uint(__uint_as_float(r[i * 4 + 3]) + b.w));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_reduce_add_2d(&tmC, stg, col_base + c * 32, row0);
-            bulk_commit();
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_acc + c * 64, r0);
-          tmem_ld32(t_acc + c * 64 + 32, r1);
-          tmem_ld_wait();
-          uint32_t pk[32];
-          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r0, p.bias + col_base + c * 64,
-                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-          bias_act_pack<EPI == ZK_EPI_BIAS_GELU_BF16>(r1, p.bias + col_base + c * 64 + 32,
-                                                      *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4), pk[i * 4 + 0], pk[i * 4 + 1], pk[i * 4 + 2],
-                         pk[i * 4 + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stg, col_base + c * 64, row0);
-            bulk_commit();
-          }
-        }
-      }
+      epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_leader(&tempty[acc]);
@@ -543,11 +588,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
-template <int EPI>
+template <int EPI, int FMT>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                        cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI>), SMEM2_BYTES, &attr_done)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI, FMT>), SMEM2_BYTES, &attr_done)) return rc;
   // persistent grid = the number of CTA pairs the device can hold at once (a TPC with one usable SM cannot host a
   // pair, so this may be less than num_sms / 2); asked from the runtime once per device
   static int resident[64] = {0};
@@ -567,113 +612,177 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.attrs = &at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI, FMT>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = num_sms() / 2;
     }
     cap = n < num_sms() / 2 ? n : num_sms() / 2;
     __atomic_store_n(&resident[dev & 63], cap, __ATOMIC_RELEASE);
-    if (getenv("ZK_DEBUG")) fprintf(stderr, "zk: %d resident CTA pairs for gemm_pair_kernel<%d>\n", cap, EPI);
+    if (getenv("ZK_DEBUG")) fprintf(stderr, "zk: %d resident CTA pairs for gemm_pair_kernel<%d, %d>\n", cap, EPI, FMT);
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = tiles < cap ? tiles : cap;
   ProfScope prof(prof_cls, stream);
-  gemm_pair_kernel<EPI><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_pair_kernel<EPI, FMT><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_pair_kernel");
   return 0;
 }
 }  // namespace pair
 
-template <int EPI>
+template <int EPI, int FMT>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                   cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<EPI>), SMEM_BYTES, &attr_done)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<EPI, FMT>), SMEM_BYTES, &attr_done)) return rc;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope prof(prof_cls, stream);
-  gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_kernel<EPI, FMT><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }
 }  // namespace gemm
 
-int gemm_bf16(const void* a, const void* w, const float* bias, void* out, long long M, int N, int K, int epilogue,
-              const float* aux, int aux_rows, cudaStream_t stream, long long out_pitch, int prof_cls) {
+int gemm16(const GemmArgs& g, cudaStream_t stream) {
   using namespace gemm;
   int rc = device_check();
   if (rc) return rc;
-  if (!a || !w || !bias || !out || M <= 0) {
-    set_error("gemm_bf16: null pointer or M <= 0");
+  const long long M = g.M;
+  const int N = g.N, K = g.K, epilogue = g.epilogue;
+  if (!g.a || !g.w || !g.bias || !g.out || M <= 0) {
+    set_error("gemm16: null pointer or M <= 0");
     return ZK_ERR_ARG;
   }
   if (N % BN || K % BK || N <= 0 || K <= 0) {
-    set_error("gemm_bf16: N (%d) must be a multiple of %d and K (%d) of %d", N, BN, K, BK);
+    set_error("gemm16: N (%d) must be a multiple of %d and K (%d) of %d", N, BN, K, BK);
     return ZK_ERR_SHAPE;
   }
-  if (epilogue == ZK_EPI_PATCH_F32 && (!aux || aux_rows <= 0)) {
-    set_error("gemm_bf16: ZK_EPI_PATCH_F32 needs the position table and patches per window");
+  if (epilogue < 0 || epilogue > ZK_EPI_BIAS_GELU_SPLIT) {
+    set_error("gemm16: unknown epilogue %d", epilogue);
     return ZK_ERR_ARG;
   }
-  if (out_pitch <= 0) out_pitch = N;
-  if (out_pitch < N || (epilogue == ZK_EPI_PATCH_F32 && out_pitch != N)) {
-    set_error("gemm_bf16: output pitch %lld < N %d", out_pitch, N);
+  if (g.fmt != FMT_BF16 && g.fmt != FMT_F16) {
+    set_error("gemm16: unknown operand format %d", g.fmt);
+    return ZK_ERR_ARG;
+  }
+  if (g.products != 1 && g.products != 3) {
+    set_error("gemm16: products must be 1 or 3 (got %d)", g.products);
+    return ZK_ERR_ARG;
+  }
+  const bool split_out = epi_is_split(epilogue);
+  if ((g.products == 3 || split_out) && g.fmt != FMT_F16) {
+    set_error("gemm16: split operands / split outputs are fp16 planes (operand format %d given)", g.fmt);
+    return ZK_ERR_ARG;
+  }
+  if (epilogue == ZK_EPI_PATCH_F32 && (!g.aux || g.aux_rows <= 0)) {
+    set_error("gemm16: ZK_EPI_PATCH_F32 needs the position table and patches per window");
+    return ZK_ERR_ARG;
+  }
+  const int planes_in = g.products == 3 ? 2 : 1;
+  const long long lda = g.lda > 0 ? g.lda : (long long)planes_in * K;
+  const long long ldw = g.ldw > 0 ? g.ldw : (long long)planes_in * K;
+  const long long out_cols = split_out ? 2LL * N : N;
+  const long long ldo = g.ldo > 0 ? g.ldo : out_cols;
+  if (lda < (long long)planes_in * K || ldw < (long long)planes_in * K || ldo < out_cols ||
+      (epilogue == ZK_EPI_PATCH_F32 && ldo != N)) {
+    set_error("gemm16: row pitches (a %lld, w %lld, out %lld) too small for K %d, N %d, %d operand plane(s)", lda, ldw, ldo, K,
+              N, planes_in);
     return ZK_ERR_SHAPE;
   }
+  const int aux_rows = g.aux_rows;
   CUtensorMap tmA, tmB, tmC;
-  if ((rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, BK))) return rc;
-  if (epilogue == ZK_EPI_BIAS_BF16 || epilogue == ZK_EPI_BIAS_GELU_BF16) {
-    if ((rc = make_tmap_bf16_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)out_pitch, 32, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmA, g.a, (uint64_t)M, (uint64_t)planes_in * K, (uint64_t)lda, BM, BK))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, g.w, (uint64_t)N, (uint64_t)planes_in * K, (uint64_t)ldw, BN, BK))) return rc;
+  if (epilogue == ZK_EPI_BIAS_BF16 || epilogue == ZK_EPI_BIAS_GELU_BF16 || split_out) {
+    if ((rc = make_tmap_bf16_2d(&tmC, g.out, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldo, 32, 64))) return rc;
   } else if (epilogue == ZK_EPI_BIAS_RESID_F32) {
-    if ((rc = make_tmap_f32_2d(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)out_pitch, 32, 32))) return rc;
+    if ((rc = make_tmap_f32_2d(&tmC, g.out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 32))) return rc;
   } else {
     // patch embedding: x viewed as [windows][patches + 2 tokens][N]
     const uint64_t windows = (uint64_t)((M + aux_rows - 1) / aux_rows);
-    if ((rc = make_tmap_f32_3d(&tmC, out, windows, (uint64_t)aux_rows + 2, (uint64_t)N, (uint64_t)N,
+    if ((rc = make_tmap_f32_3d(&tmC, g.out, windows, (uint64_t)aux_rows + 2, (uint64_t)N, (uint64_t)N,
                                (uint64_t)(aux_rows + 2) * N, 32, 32)))
       return rc;
   }
   Params p;
-  p.bias = bias;
-  p.out = out;
-  p.aux = aux;
+  p.bias = g.bias;
+  p.out = g.out;
+  p.aux = g.aux;
   p.M = M;
   p.N = N;
   p.K = K;
   p.aux_rows = aux_rows;
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = N / BN;
+  p.acc_scale = g.acc_scale;
+  p.nprod = g.products;
+  p.out_plane_stride = N;
+  if (g.products == 3) {  // smallest terms first: A_lo W_hi, A_hi W_lo, A_hi W_hi
+    p.a_off[0] = K, p.w_off[0] = 0;
+    p.a_off[1] = 0, p.w_off[1] = K;
+    p.a_off[2] = 0, p.w_off[2] = 0;
+  } else {
+    for (int i = 0; i < MAX_PRODUCTS; ++i) p.a_off[i] = p.w_off[i] = 0;
+  }
+  const int prof_cls = g.prof_cls;
   const auto cls = [&](int by_epilogue) { return prof_cls >= 0 ? prof_cls : by_epilogue; };
+  const int cls_resid = K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT;
   // CTA-pair tiles for the large GEMMs (ZK_GEMM_PAIR: 0 = never, 1 = all but fc1, 2 = all, the default).  With the
   // two-MUFU GELU the fc1 epilogue paced its tile and pair tiles did not pay; with the one-MUFU form they do
   // (0.586 against 0.606 ms at M = 155 392 on the same box).
   static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 2;
+  const bool f16 = g.fmt == FMT_F16;
   if (use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2)) {
-    if ((rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, 128, BK))) return rc;  // half W tiles
+    if ((rc = make_tmap_bf16_2d(&tmB, g.w, (uint64_t)N, (uint64_t)planes_in * K, (uint64_t)ldw, 128, BK))) return rc;  // half W tiles
     p.num_m_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
     switch (epilogue) {
-      case ZK_EPI_BIAS_BF16: return pair::launch_pair<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
+      case ZK_EPI_BIAS_BF16:
+        return f16 ? pair::launch_pair<ZK_EPI_BIAS_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream)
+                   : pair::launch_pair<ZK_EPI_BIAS_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
       case ZK_EPI_BIAS_GELU_BF16:
-        return pair::launch_pair<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
+        return f16 ? pair::launch_pair<ZK_EPI_BIAS_GELU_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream)
+                   : pair::launch_pair<ZK_EPI_BIAS_GELU_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
       case ZK_EPI_BIAS_RESID_F32:
-        return pair::launch_pair<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, cls(K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT), stream);
+        return f16 ? pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16>(tmA, tmB, tmC, p, cls(cls_resid), stream)
+                   : pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(cls_resid), stream);
+      case ZK_EPI_BIAS_SPLIT: return pair::launch_pair<ZK_EPI_BIAS_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);
+      case ZK_EPI_BIAS_GELU_SPLIT:
+        return pair::launch_pair<ZK_EPI_BIAS_GELU_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);
     }
   }
   switch (epilogue) {
-    case ZK_EPI_BIAS_BF16: return launch<ZK_EPI_BIAS_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
-    case ZK_EPI_BIAS_GELU_BF16: return launch<ZK_EPI_BIAS_GELU_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
+    case ZK_EPI_BIAS_BF16:
+      return f16 ? launch<ZK_EPI_BIAS_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream)
+                 : launch<ZK_EPI_BIAS_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_QKV), stream);
+    case ZK_EPI_BIAS_GELU_BF16:
+      return f16 ? launch<ZK_EPI_BIAS_GELU_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream)
+                 : launch<ZK_EPI_BIAS_GELU_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
     case ZK_EPI_BIAS_RESID_F32:
-      return launch<ZK_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, p, cls(K > 768 ? ZK_K_GEMM_FC2 : ZK_K_GEMM_OUT), stream);
-    case ZK_EPI_PATCH_F32: return launch<ZK_EPI_PATCH_F32>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_PATCH), stream);
+      return f16 ? launch<ZK_EPI_BIAS_RESID_F32, FMT_F16>(tmA, tmB, tmC, p, cls(cls_resid), stream)
+                 : launch<ZK_EPI_BIAS_RESID_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(cls_resid), stream);
+    case ZK_EPI_PATCH_F32:
+      return f16 ? launch<ZK_EPI_PATCH_F32, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_PATCH), stream)
+                 : launch<ZK_EPI_PATCH_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_PATCH), stream);
+    case ZK_EPI_BIAS_SPLIT: return launch<ZK_EPI_BIAS_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);
+    case ZK_EPI_BIAS_GELU_SPLIT: return launch<ZK_EPI_BIAS_GELU_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);
   }
-  set_error("gemm_bf16: unknown epilogue %d", epilogue);
+  set_error("gemm16: unknown epilogue %d", epilogue);
   return ZK_ERR_ARG;
 }
 
 }  // namespace zk
 
+extern "C" int zk_gemm16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_out,
+                         int64_t ldo, int64_t M, int N, int K, int epilogue, int operand_format, int products,
+                         float acc_scale, const float* d_aux, int aux_rows, zk_stream_t stream) {
+  zk::GemmArgs g;
+  g.a = d_a, g.lda = lda, g.w = d_w, g.ldw = ldw, g.bias = d_bias, g.out = d_out, g.ldo = ldo;
+  g.M = M, g.N = N, g.K = K, g.epilogue = epilogue, g.fmt = operand_format, g.products = products;
+  g.acc_scale = acc_scale, g.aux = d_aux, g.aux_rows = aux_rows, g.prof_cls = -1;
+  return zk::gemm16(g, (cudaStream_t)stream);
+}
+
 extern "C" int zk_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int64_t M, int N, int K,
                             int epilogue, const float* d_aux, int aux_rows, zk_stream_t stream) {
-  return zk::gemm_bf16(d_a, d_w, d_bias, d_out, M, N, K, epilogue, d_aux, aux_rows, (cudaStream_t)stream, 0, -1);
+  return zk_gemm16(d_a, 0, d_w, 0, d_bias, d_out, 0, M, N, K, epilogue, ZK_FMT_BF16, 1, 1.0f, d_aux, aux_rows, stream);
 }

@@ -8,6 +8,7 @@
 
 #include "zk_b200.h"
 #include "zk_common.cuh"
+#include "zk_internal.cuh"
 
 namespace zk {
 
@@ -185,7 +186,12 @@ static cudaEvent_t prof_event() {
   return e;
 }
 
+static thread_local int g_prof_override = -1;
+ProfClassOverride::ProfClassOverride(int cls) : prev_(g_prof_override) { g_prof_override = cls; }
+ProfClassOverride::~ProfClassOverride() { g_prof_override = prev_; }
+
 ProfScope::ProfScope(int cls, cudaStream_t stream) : cls_(cls), stream_(stream), stop_(nullptr) {
+  if (g_prof_override >= 0) cls = cls_ = g_prof_override;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_count[cls]++;
   if (!g_prof_time) return;
@@ -229,7 +235,7 @@ int zk_prof_collect(float* ms, int64_t* launches) {
 const char* zk_kernel_class_name(int cls) {
   static const char* names[ZK_K_NUM_CLASSES] = {"resample", "fbank", "gather_patches", "gemm_patch", "layernorm",
                                                "gemm_qkv", "attention", "gemm_out", "gemm_fc1", "gemm_fc2",
-                                               "head", "gate", "misc", "last_layer_tail"};
+                                               "head", "gate", "misc", "last_layer_tail", "recheck"};
   return (cls >= 0 && cls < ZK_K_NUM_CLASSES) ? names[cls] : "?";
 }
 

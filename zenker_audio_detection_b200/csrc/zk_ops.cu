@@ -43,13 +43,81 @@ int f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
   return 0;
 }
 
+// f32 [rows][cols] * scale -> 16-bit [rows][planes * cols]; planes == 2 writes the fp16 hi plane at columns [0, cols)
+// and the lo plane (x - hi) at [cols, 2 cols): the operand layout of the split-operand GEMM (zk_gemm.cu).
+__global__ void f32_to_16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long rows, int cols, int fmt,
+                                 int planes, float scale) {
+  const long long groups = rows * (long long)(cols >> 2);
+  const int gpr = cols >> 2;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const long long row = g / gpr;
+    const int c = (int)(g - row * gpr) * 4;
+    float4 v = *reinterpret_cast<const float4*>(in + row * cols + c);
+    v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+    uint16_t* o = out + row * (long long)planes * cols + c;
+    if (planes == 2) {
+      uint2 hi, lo;
+      split_f16_pair(v.x, v.y, hi.x, lo.x);
+      split_f16_pair(v.z, v.w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(o) = hi;
+      *reinterpret_cast<uint2*>(o + cols) = lo;
+    } else {
+      uint2 q;
+      q.x = pack16_rt(fmt, v.x, v.y);
+      q.y = pack16_rt(fmt, v.z, v.w);
+      *reinterpret_cast<uint2*>(o) = q;
+    }
+  }
+}
+
+int f32_to_16(const float* in, void* out, long long rows, int cols, int fmt, int planes, float scale, cudaStream_t stream) {
+  if (!in || !out || rows < 0 || cols <= 0 || (cols & 3) || (planes != 1 && planes != 2) || (planes == 2 && fmt != FMT_F16) ||
+      (fmt != FMT_F16 && fmt != FMT_BF16)) {
+    set_error("f32_to_16: bad arguments (cols %d must be a multiple of 4; two planes are fp16 only)", cols);
+    return ZK_ERR_ARG;
+  }
+  if (rows == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) {
+    set_error("f32_to_16: pointers must be 16-byte (in) / 8-byte (out) aligned");
+    return ZK_ERR_ARG;
+  }
+  long long groups = rows * (cols / 4);
+  long long blocks = (groups + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ProfScope prof(ZK_K_MISC, stream);
+  f32_to_16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<uint16_t*>(out), rows, cols, fmt, planes, scale);
+  ZK_LAUNCH_CHECK("f32_to_16_kernel");
+  return 0;
+}
+
+// max |x| (model creation: the power-of-two scale of a weight matrix); non-negative floats order like their bit patterns
+__global__ void max_abs_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(in[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+int max_abs(const float* in, long long n, float* d_out, cudaStream_t stream) {
+  ZK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), stream));
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  max_abs_kernel<<<(int)blocks, 256, 0, stream>>>(in, n, d_out);
+  ZK_LAUNCH_CHECK("max_abs_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ layernorm
 // One warp per row of 768 fp32 (HF:modeling_audio_spectrogram_transformer.py:260-261,268,275): two-pass
-// mean / biased variance in registers, fp32 math, bf16 result (the A operand of the next GEMM).
+// mean / biased variance in registers, fp32 math, 16-bit result (the A operand of the next GEMM); PLANES == 2 writes
+// fp16 hi | lo planes (row pitch 1536) for the split-operand path.
 constexpr int LN_COLS = 768;
+template <int FMT, int PLANES>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps,
-                                                        __nv_bfloat16* __restrict__ out, long long rows) {
+                                                        uint16_t* __restrict__ out, long long rows) {
   const int lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long row_stride = (long long)gridDim.x * (blockDim.x >> 5);
@@ -73,38 +141,53 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / LN_COLS) + eps);
-    uint2* orow = reinterpret_cast<uint2*>(out + row * LN_COLS);
+    uint2* orow = reinterpret_cast<uint2*>(out + row * (LN_COLS * PLANES));
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
-      uint2 o;
-      o.x = pack_bf16(v[i].x * rstd * g.x + bb.x, v[i].y * rstd * g.y + bb.y);
-      o.y = pack_bf16(v[i].z * rstd * g.z + bb.z, v[i].w * rstd * g.w + bb.w);
-      orow[lane + 32 * i] = o;
+      const float y0 = v[i].x * rstd * g.x + bb.x, y1 = v[i].y * rstd * g.y + bb.y;
+      const float y2 = v[i].z * rstd * g.z + bb.z, y3 = v[i].w * rstd * g.w + bb.w;
+      if constexpr (PLANES == 2) {
+        uint2 hi, lo;
+        split_f16_pair(y0, y1, hi.x, lo.x);
+        split_f16_pair(y2, y3, hi.y, lo.y);
+        orow[lane + 32 * i] = hi;
+        orow[LN_COLS / 4 + lane + 32 * i] = lo;
+      } else {
+        uint2 o;
+        o.x = pack16<FMT>(y0, y1);
+        o.y = pack16<FMT>(y2, y3);
+        orow[lane + 32 * i] = o;
+      }
     }
   }
 }
 
-int layernorm_bf16(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols,
-                   cudaStream_t stream) {
-  return layernorm_bf16_cls(x, w, b, eps, out, rows, cols, ZK_K_LAYERNORM, stream);
-}
-
-int layernorm_bf16_cls(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols,
-                       int prof_cls, cudaStream_t stream) {
+int layernorm16(const float* x, const float* w, const float* b, float eps, void* out, long long rows, int cols, int fmt,
+                int planes, int prof_cls, cudaStream_t stream) {
   if (!x || !w || !b || !out || rows <= 0) {
-    set_error("layernorm_bf16: bad arguments");
+    set_error("layernorm16: bad arguments");
     return ZK_ERR_ARG;
   }
   if (cols != LN_COLS) {
-    set_error("layernorm_bf16: cols must be %d (got %d)", LN_COLS, cols);
+    set_error("layernorm16: cols must be %d (got %d)", LN_COLS, cols);
     return ZK_ERR_SHAPE;
+  }
+  if ((fmt != FMT_F16 && fmt != FMT_BF16) || (planes != 1 && planes != 2) || (planes == 2 && fmt != FMT_F16)) {
+    set_error("layernorm16: operand format %d with %d plane(s) is not supported (two planes are fp16)", fmt, planes);
+    return ZK_ERR_ARG;
   }
   long long blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  ProfScope prof(prof_cls, stream);
-  layernorm_kernel<<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
+  ProfScope prof(prof_cls < 0 ? ZK_K_LAYERNORM : prof_cls, stream);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  if (planes == 2)
+    layernorm_kernel<FMT_F16, 2><<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, o, rows);
+  else if (fmt == FMT_F16)
+    layernorm_kernel<FMT_F16, 1><<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, o, rows);
+  else
+    layernorm_kernel<FMT_BF16, 1><<<(int)blocks, 256, 0, stream>>>(x, w, b, eps, o, rows);
   ZK_LAUNCH_CHECK("layernorm_kernel");
   return 0;
 }
@@ -133,9 +216,12 @@ int gather_head_rows(const void* h, const float* x, int batch, int tokens, void*
 }
 
 constexpr int AH_THREADS = 256, AH_HEADS = 12, AH_D = 64, AH_QKV = 3 * LN_COLS;
-__global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const __nv_bfloat16* __restrict__ q2,
-                                                                         const __nv_bfloat16* __restrict__ qkv,
-                                                                         __nv_bfloat16* __restrict__ out2, int tokens) {
+__device__ __forceinline__ float load16_rt(int fmt, const uint16_t* p) {
+  return fmt == FMT_F16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __uint_as_float((uint32_t)*p << 16);
+}
+__global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const uint16_t* __restrict__ q2,
+                                                                         const uint16_t* __restrict__ qkv,
+                                                                         uint16_t* __restrict__ out2, int tokens, int fmt) {
   extern __shared__ float ah_sm[];  // scores [2][tokens], then q [2][64], reduction scratch
   float* sc = ah_sm;
   float* qs = ah_sm + 2 * tokens;
@@ -143,10 +229,10 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
   if (tid < 2 * AH_D)
-    qs[tid] = __bfloat162float(q2[(long long)(2 * b + (tid >> 6)) * LN_COLS + h * AH_D + (tid & 63)]) * SCALE_LOG2E;
+    qs[tid] = load16_rt(fmt, q2 + (long long)(2 * b + (tid >> 6)) * LN_COLS + h * AH_D + (tid & 63)) * SCALE_LOG2E;
   __syncthreads();
-  const __nv_bfloat16* kbase = qkv + (long long)b * tokens * AH_QKV + LN_COLS + h * AH_D;
-  const __nv_bfloat16* vbase = kbase + LN_COLS;
+  const uint16_t* kbase = qkv + (long long)b * tokens * AH_QKV + LN_COLS + h * AH_D;
+  const uint16_t* vbase = kbase + LN_COLS;
   float m0 = -INFINITY, m1 = -INFINITY;
   for (int key = tid; key < tokens; key += AH_THREADS) {
     const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * AH_QKV);
@@ -157,7 +243,8 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+        const float2 kv = unpack16_rt(fmt, w[j]);
+        const float lo = kv.x, hi = kv.y;
         const int d = i * 8 + j * 2;
         d0 = fmaf(lo, qs[d], fmaf(hi, qs[d + 1], d0));
         d1 = fmaf(lo, qs[AH_D + d], fmaf(hi, qs[AH_D + d + 1], d1));
@@ -208,7 +295,7 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
   __syncthreads();
   // o[qi][d] = sum_key p[qi][key] V[key][d]: warp w takes keys w, w + 8, ...; lane l owns dims 2 l, 2 l + 1, so one
   // warp instruction reads one whole 128-byte V row; four keys in flight per iteration, partials reduced over the warps
-  const __nv_bfloat16* vrow = vbase + 2 * lane;
+  const uint16_t* vrow = vbase + 2 * lane;
   float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
   int key = warp;
   for (; key + 24 < tokens; key += 32) {
@@ -217,7 +304,8 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
     for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint32_t*>(vrow + (long long)(key + 8 * u) * AH_QKV));
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float lo = __uint_as_float(v[u] << 16), hi = __uint_as_float(v[u] & 0xffff0000u);
+      const float2 vv = unpack16_rt(fmt, v[u]);
+      const float lo = vv.x, hi = vv.y;
       const float p0 = sc[key + 8 * u], p1 = sc[tokens + key + 8 * u];
       a00 = fmaf(p0, lo, a00);
       a01 = fmaf(p0, hi, a01);
@@ -227,7 +315,8 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
   }
   for (; key < tokens; key += 8) {
     const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(vrow + (long long)key * AH_QKV));
-    const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+    const float2 vv = unpack16_rt(fmt, v);
+    const float lo = vv.x, hi = vv.y;
     const float p0 = sc[key], p1 = sc[tokens + key];
     a00 = fmaf(p0, lo, a00);
     a01 = fmaf(p0, hi, a01);
@@ -245,11 +334,12 @@ __global__ void __launch_bounds__(AH_THREADS) attention_head_rows_kernel(const _
     float o = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) o += part[(w * 2 + qi) * AH_D + d];
-    out2[(long long)(2 * b + qi) * LN_COLS + h * AH_D + d] = __float2bfloat16(o / (qi ? l1 : l0));
+    const float r = o / (qi ? l1 : l0);
+    out2[(long long)(2 * b + qi) * LN_COLS + h * AH_D + d] = (uint16_t)(pack16_rt(fmt, r, 0.f) & 0xffffu);
   }
 }
 
-int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, int tokens, cudaStream_t stream) {
+int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, int tokens, int fmt, cudaStream_t stream) {
   const size_t smem = (size_t)(2 * tokens + 2 * AH_D + 16 * AH_D) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("attention_head_rows: %d tokens do not fit the score buffer", tokens);
@@ -259,8 +349,8 @@ int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, 
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_head_rows_kernel), 200 * 1024, &attr_done)) return rc;
   ProfScope prof(ZK_K_TAIL, stream);
   attention_head_rows_kernel<<<dim3(AH_HEADS, batch), AH_THREADS, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q2), reinterpret_cast<const __nv_bfloat16*>(qkv),
-      reinterpret_cast<__nv_bfloat16*>(out2), tokens);
+      reinterpret_cast<const uint16_t*>(q2), reinterpret_cast<const uint16_t*>(qkv), reinterpret_cast<uint16_t*>(out2),
+      tokens, fmt);
   ZK_LAUNCH_CHECK("attention_head_rows_kernel");
   return 0;
 }
@@ -271,7 +361,7 @@ int attention_head_rows(const void* q2, const void* qkv, void* out2, int batch, 
 // flattened frequency-major (patch p = f*nt + t), weight[o][0][kf][kt].
 // One warp per patch; lane = (kf, half of kt): 8 loads along time, one 16-byte store.
 __global__ void __launch_bounds__(256) gather_kernel(GatherSrc src, int batch, int max_length, int nt,
-                                                     __nv_bfloat16* __restrict__ a) {
+                                                     uint16_t* __restrict__ a, int fmt, int planes) {
   const int lane = threadIdx.x & 31;
   const int kf = lane >> 1, kt0 = (lane & 1) * 8;
   const long long patches = (long long)batch * 12 * nt;
@@ -285,7 +375,8 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherSrc src, int batch, i
     const int col = 10 * f + kf;
     float v[8];
     if (src.features) {
-      const float* xb = src.features + ((long long)bwin * max_length + 10 * t + kt0) * 128 + col;
+      const long long frow = src.window_index ? (long long)src.window_index[bwin] : (long long)bwin;
+      const float* xb = src.features + (frow * max_length + 10 * t + kt0) * 128 + col;
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = __ldg(xb + i * 128);
     } else {
@@ -300,22 +391,33 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherSrc src, int batch, i
         v[i] = x;
       }
     }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]);
-    o.y = pack_bf16(v[2], v[3]);
-    o.z = pack_bf16(v[4], v[5]);
-    o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(a + p * 256 + kf * 16 + kt0) = o;
+    uint16_t* dst = a + p * (256 * planes) + kf * 16 + kt0;
+    if (planes == 2) {  // fp16 hi | lo planes, row pitch 512
+      uint4 hi, lo;
+      split_f16_pair(v[0], v[1], hi.x, lo.x);
+      split_f16_pair(v[2], v[3], hi.y, lo.y);
+      split_f16_pair(v[4], v[5], hi.z, lo.z);
+      split_f16_pair(v[6], v[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + 256) = lo;
+    } else {
+      uint4 o;
+      o.x = pack16_rt(fmt, v[0], v[1]);
+      o.y = pack16_rt(fmt, v[2], v[3]);
+      o.z = pack16_rt(fmt, v[4], v[5]);
+      o.w = pack16_rt(fmt, v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    }
   }
 }
 
-int gather_patches(const GatherSrc& src, int batch, int max_length, void* a_out, cudaStream_t stream) {
+int gather_patches(const GatherSrc& src, int batch, int max_length, void* a_out, int fmt, int planes, cudaStream_t stream) {
   const int nt = (max_length - 16) / 10 + 1;
   long long patches = (long long)batch * 12 * nt;
   long long blocks = (patches + 7) / 8;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ProfScope prof(ZK_K_GATHER, stream);
-  gather_kernel<<<(int)blocks, 256, 0, stream>>>(src, batch, max_length, nt, reinterpret_cast<__nv_bfloat16*>(a_out));
+  gather_kernel<<<(int)blocks, 256, 0, stream>>>(src, batch, max_length, nt, reinterpret_cast<uint16_t*>(a_out), fmt, planes);
   ZK_LAUNCH_CHECK("gather_kernel");
   return 0;
 }
@@ -514,6 +616,64 @@ __global__ void __launch_bounds__(1024) gate_compact_kernel(const float* __restr
   if (threadIdx.x == 0) *count = base_s;
 }
 
+// Decision re-check selection (order-preserving compaction, same single-block scan as the gate): row i is selected when
+// its margin l1 - l0 lies within eps of one of the decision points.  The FAST forward's logit error is bounded by eps
+// (measured), so every window outside the band already has the reference's decision.
+struct BandMargins {
+  float m[4];
+  int n;
+};
+__global__ void __launch_bounds__(1024) band_select_kernel(const float* __restrict__ logits, int n, BandMargins mg, float eps,
+                                                           const int32_t* __restrict__ src_window, int32_t* __restrict__ pos,
+                                                           int32_t* __restrict__ window, int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + threadIdx.x;
+    bool sel = false;
+    if (i < n) {
+      const float d = logits[2 * i + 1] - logits[2 * i];
+      for (int j = 0; j < mg.n; ++j) sel = sel || !(fabsf(d - mg.m[j]) > eps);  // NaN margins are re-checked too
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    {
+      int v = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += y;
+      }
+      off = __shfl_sync(0xffffffffu, v, warp) - warp_tot[warp];
+      tot = __shfl_sync(0xffffffffu, v, 31);
+    }
+    const int base = base_s;
+    if (sel) {
+      pos[base + off + within] = i;
+      window[base + off + within] = src_window ? src_window[i] : i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = base + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
+__global__ void scatter_rows2_kernel(const float* __restrict__ src, const int32_t* __restrict__ pos, int count,
+                                     float* __restrict__ dst) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const int i = pos[j];
+  dst[2 * i] = src[2 * j];
+  dst[2 * i + 1] = src[2 * j + 1];
+}
+
 __global__ void softmax2_kernel(const float* __restrict__ logits, int n, float* __restrict__ probs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -531,11 +691,55 @@ int zk_f32_to_bf16(const float* d_in, void* d_out, int64_t n, zk_stream_t stream
   return zk::f32_to_bf16(d_in, d_out, n, (cudaStream_t)stream);
 }
 
-int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows,
-                      int cols, zk_stream_t stream) {
+int zk_f32_to_16(const float* d_in, void* d_out, int64_t rows, int cols, int operand_format, int planes, float scale,
+                 zk_stream_t stream) {
   int rc = zk::device_check();
   if (rc) return rc;
-  return zk::layernorm_bf16(d_x, d_w, d_b, eps, d_out, rows, cols, (cudaStream_t)stream);
+  return zk::f32_to_16(d_in, d_out, rows, cols, operand_format, planes, scale, (cudaStream_t)stream);
+}
+
+int zk_layernorm16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows, int cols,
+                   int operand_format, int planes, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  return zk::layernorm16(d_x, d_w, d_b, eps, d_out, rows, cols, operand_format, planes, -1, (cudaStream_t)stream);
+}
+
+int zk_layernorm_bf16(const float* d_x, const float* d_w, const float* d_b, float eps, void* d_out, int64_t rows,
+                      int cols, zk_stream_t stream) {
+  return zk_layernorm16(d_x, d_w, d_b, eps, d_out, rows, cols, ZK_FMT_BF16, 1, stream);
+}
+
+int zk_band_select(const float* d_logits, int n, const float* h_margins, int num_margins, float eps,
+                   const int32_t* d_src_window, int32_t* d_pos, int32_t* d_window, int32_t* d_count, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (n < 0 || !d_count || num_margins < 0 || num_margins > 4 || (num_margins > 0 && !h_margins) || !(eps >= 0.f) ||
+      (n > 0 && (!d_logits || !d_pos || !d_window))) {
+    zk::set_error("zk_band_select: bad arguments (at most 4 decision points, eps >= 0)");
+    return ZK_ERR_ARG;
+  }
+  zk::BandMargins mg;
+  mg.n = num_margins;
+  for (int i = 0; i < 4; ++i) mg.m[i] = i < num_margins ? h_margins[i] : 0.f;
+  zk::ProfScope prof(ZK_K_GATE, (cudaStream_t)stream);
+  zk::band_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_logits, n, mg, eps, d_src_window, d_pos, d_window, d_count);
+  ZK_LAUNCH_CHECK("band_select_kernel");
+  return 0;
+}
+
+int zk_scatter_rows2(const float* d_src, const int32_t* d_pos, int count, float* d_dst, zk_stream_t stream) {
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!d_src || !d_pos || !d_dst))) {
+    zk::set_error("zk_scatter_rows2: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  if (count == 0) return 0;
+  zk::ProfScope prof(ZK_K_GATE, (cudaStream_t)stream);
+  zk::scatter_rows2_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_src, d_pos, count, d_dst);
+  ZK_LAUNCH_CHECK("scatter_rows2_kernel");
+  return 0;
 }
 
 int zk_gate_compact(const float* d_logits, int n, float threshold, float min_prob, float* d_probs, int32_t* d_pred,

@@ -54,7 +54,7 @@ class ZenkerASTFeatureExtractor:
         self.do_normalize = do_normalize
         self.mean = mean
         self.std = std
-        self._plan: Optional[ops.FbankPlan] = None
+        self._plan: dict = {}  # device index -> ops.FbankPlan
 
     # ------------------------------------------------------------------ (de)serialisation
     @classmethod
@@ -93,10 +93,20 @@ class ZenkerASTFeatureExtractor:
         return f"{self.__class__.__name__} {self.to_json_string()}"
 
     # ------------------------------------------------------------------ compute
-    def _get_plan(self) -> ops.FbankPlan:
-        if self._plan is None or self._plan.num_mel_bins != self.num_mel_bins:
-            self._plan = ops.FbankPlan("hanning", self.num_mel_bins)  # HF:...:116-121 window_type="hanning"
-        return self._plan
+    def _get_plan(self, device: Optional[torch.device] = None) -> ops.FbankPlan:
+        """The fbank tables for ``device`` (default: the current CUDA device); one plan per device, because the tables
+        live in that device's memory (zk_fbank_f32 rejects a plan from another device)."""
+        idx = torch.device(device).index if device is not None else None
+        if idx is None:
+            idx = torch.cuda.current_device()
+        if not isinstance(self._plan, dict):
+            self._plan = {}
+        plan = self._plan.get(idx)
+        if plan is None or plan.num_mel_bins != self.num_mel_bins:
+            with torch.cuda.device(idx):
+                plan = ops.FbankPlan("hanning", self.num_mel_bins)  # HF:...:116-121 window_type="hanning"
+            self._plan[idx] = plan
+        return plan
 
     def features_cuda(self, raw: List[np.ndarray]) -> torch.Tensor:
         """(B, max_length, num_mel_bins) float32 CUDA tensor for a list of mono float32 waveforms."""

@@ -8,6 +8,7 @@ The forward runs in libzk_b200 (``zk_model_forward``); there is no PyTorch fallb
 from __future__ import annotations
 
 import json
+import math
 import os
 from types import SimpleNamespace
 from typing import Any, Dict, Optional
@@ -46,8 +47,43 @@ def _cfg_get(cfg: Any, name: str, default=None):
     return getattr(cfg, name, default)
 
 
+# Half-width (logit units) of the band around a decision threshold inside which a window is re-run at
+# PRECISION_RECHECK.  It has to cover the FAST path's logit error: measured max 3e-3 (fp16 operands) / 1.9e-2 (bf16)
+# on the conditioned random-init weights, hence the two defaults.  ZK_RECHECK_EPS overrides.
+RECHECK_EPS = {"fp16": 8e-3, "bf16": 4e-2}
+
+
+def default_recheck_eps(operand_format: str) -> float:
+    v = os.environ.get("ZK_RECHECK_EPS")
+    return float(v) if v not in (None, "") else RECHECK_EPS["bf16" if operand_format.startswith("b") else "fp16"]
+
+
+def logit(p: float) -> float:
+    """Margin ``l1 - l0`` at which ``softmax([l0, l1])[1] == p``; +-inf at the ends (such a threshold has no band)."""
+    p = float(p)
+    if p <= 0.0:
+        return -math.inf
+    if p >= 1.0:
+        return math.inf
+    return math.log(p / (1.0 - p))
+
+
+def decision_margins(thresholds) -> list:
+    """Finite, de-duplicated decision points (logit units) for a set of probability thresholds on class 1."""
+    out = []
+    for t in thresholds:
+        if t is None:
+            continue
+        m = logit(t)
+        if math.isfinite(m) and all(abs(m - o) > 1e-12 for o in out):
+            out.append(m)
+    if len(out) > 4:
+        raise ZkError("at most 4 distinct decision thresholds per stage are supported by zk_band_select")
+    return out
+
+
 class ZenkerASTForAudioClassification:
-    def __init__(self, config: Any, state_dict: Dict[str, torch.Tensor]):
+    def __init__(self, config: Any, state_dict: Dict[str, torch.Tensor], operand_format: Optional[str] = None):
         for k, v in _GEOMETRY.items():
             got = _cfg_get(config, k, v)
             if got != v:
@@ -63,10 +99,20 @@ class ZenkerASTForAudioClassification:
         self.device = torch.device("cpu")
         self._engine: Optional[ops.AstModel] = None
         self.training = False
+        self.operand_format = (operand_format or ops.default_operand_format()).lower()
+        # Decision re-check inside __call__ (the reference thresholds the returned scores on the host, ref:312-320):
+        # windows whose FAST margin is within recheck_eps of a decision point are recomputed at fp32-class precision
+        # before the logits are returned.  The decision points default to argmax / p = 0.5 (the scripts' default
+        # thresholds, ref:226-227); a caller running other thresholds sets them (or ZK_RECHECK_THRESHOLDS=0.6,0.35).
+        env_thr = os.environ.get("ZK_RECHECK_THRESHOLDS")
+        self.recheck_thresholds = [float(t) for t in env_thr.split(",")] if env_thr else [0.5]
+        self.recheck_eps = default_recheck_eps(self.operand_format)
+        self.last_rechecked = 0
 
     # ------------------------------------------------------------------ loading
     @classmethod
-    def from_pretrained(cls, pretrained_model_name_or_path: str, config: Any = None, **kwargs):
+    def from_pretrained(cls, pretrained_model_name_or_path: str, config: Any = None, operand_format: Optional[str] = None,
+                        **kwargs):
         root = pretrained_model_name_or_path
         if config is None:
             path = os.path.join(root, CONFIG_NAME)
@@ -83,7 +129,7 @@ class ZenkerASTForAudioClassification:
             sd = torch.load(binf, map_location="cpu", weights_only=True)
         else:
             raise OSError(f"no {WEIGHTS_SAFE} or {WEIGHTS_BIN} under {root}")
-        return cls(config, sd)
+        return cls(config, sd, operand_format=operand_format)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return dict(self._sd)
@@ -99,7 +145,8 @@ class ZenkerASTForAudioClassification:
             device = torch.device("cuda", torch.cuda.current_device())
         if self._engine is None or self.device != device:
             with torch.cuda.device(device):
-                self._engine = ops.AstModel(self._sd, self.max_length, self.num_labels, self.ln_eps, device=device)
+                self._engine = ops.AstModel(self._sd, self.max_length, self.num_labels, self.ln_eps, device=device,
+                                            operand_format=self.operand_format)
             self.device = device
         return self
 
@@ -137,6 +184,10 @@ class ZenkerASTForAudioClassification:
             x = x.float()
         with torch.cuda.device(self.device):
             logits = eng.forward_features(x)
+            self.last_rechecked = 0
+            if self.num_labels == 2 and self.recheck_eps > 0:
+                self.last_rechecked = eng.recheck_features(x, logits, decision_margins(self.recheck_thresholds),
+                                                           self.recheck_eps)
         return SequenceClassifierOutput(logits)
 
     __call__ = forward

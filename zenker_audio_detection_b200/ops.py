@@ -132,42 +132,87 @@ class FbankPlan:
 
 
 # ------------------------------------------------------------------------------------------ building blocks
-def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, out: Optional[torch.Tensor] = None,
-         aux: Optional[torch.Tensor] = None, aux_rows: int = 0) -> torch.Tensor:
+_DT = {_lib.FMT_BF16: torch.bfloat16, _lib.FMT_F16: torch.float16}
+
+
+def _fmt_of(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.bfloat16:
+        return _lib.FMT_BF16
+    if t.dtype == torch.float16:
+        return _lib.FMT_F16
+    raise ZkError(f"{name}: expected a bfloat16 or float16 tensor, got {t.dtype}")
+
+
+def split_f16(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """CUDA fp32 ``(rows, cols)`` -> fp16 ``(rows, 2*cols)`` = hi | lo planes of ``x*scale`` (split-operand layout)."""
     lib = _lib.load()
-    a = _cuda(a, torch.bfloat16, "gemm a")
-    w = _cuda(w, torch.bfloat16, "gemm w")
-    bias = _cuda(bias, torch.float32, "gemm bias")
-    M, K = a.shape
-    N = w.shape[0]
-    if out is None:
-        if epilogue in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16):
-            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-        else:
-            raise ZkError("gemm: the fp32 epilogues accumulate into / scatter to a caller-provided `out`")
-    check(lib.zk_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, epilogue,
-                           aux.data_ptr() if aux is not None else None, aux_rows, _lib.stream_ptr()), "zk_gemm_bf16")
+    x = _cuda(x, torch.float32, "split_f16")
+    rows, cols = x.shape
+    out = torch.empty((rows, 2 * cols), dtype=torch.float16, device=x.device)
+    check(lib.zk_f32_to_16(x.data_ptr(), out.data_ptr(), rows, cols, _lib.FMT_F16, 2, float(scale), _lib.stream_ptr()),
+          "zk_f32_to_16")
     return out
 
 
-def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, out: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, aux_rows: int = 0, products: int = 1, acc_scale: float = 1.0) -> torch.Tensor:
+    """``epilogue(a @ w.T * acc_scale + bias)`` on the tcgen05 GEMM.  ``a`` (M, planes*K), ``w`` (N, planes*K) in bf16 or
+    fp16; ``products == 3``: fp16 hi | lo planes (planes = 2) and the three-product sum."""
+    lib = _lib.load()
+    fmt = _fmt_of(a, "gemm a")
+    a = _cuda(a, _DT[fmt], "gemm a")
+    w = _cuda(w, _DT[fmt], "gemm w")
+    bias = _cuda(bias, torch.float32, "gemm bias")
+    planes = 2 if products == 3 else 1
+    M, K = a.shape[0], a.shape[1] // planes
+    N = w.shape[0]
+    if w.shape[1] != planes * K:
+        raise ZkError(f"gemm: a is (M, {a.shape[1]}) but w is (N, {w.shape[1]})")
+    if out is None:
+        if epilogue in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16):
+            out = torch.empty((M, N), dtype=_DT[fmt], device=a.device)
+        elif epilogue in (_lib.EPI_BIAS_SPLIT, _lib.EPI_BIAS_GELU_SPLIT):
+            out = torch.empty((M, 2 * N), dtype=torch.float16, device=a.device)
+        else:
+            raise ZkError("gemm: the fp32 epilogues accumulate into / scatter to a caller-provided `out`")
+    check(lib.zk_gemm16(a.data_ptr(), 0, w.data_ptr(), 0, bias.data_ptr(), out.data_ptr(), 0, M, N, K, epilogue, fmt,
+                        products, float(acc_scale), aux.data_ptr() if aux is not None else None, aux_rows,
+                        _lib.stream_ptr()), "zk_gemm16")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, dtype: torch.dtype = torch.bfloat16,
+              planes: int = 1) -> torch.Tensor:
     lib = _lib.load()
     x = _cuda(x, torch.float32, "layernorm x")
     rows, cols = x.shape
-    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
-    check(lib.zk_layernorm_bf16(x.data_ptr(), _cuda(w, torch.float32, "w").data_ptr(),
-                                _cuda(b, torch.float32, "b").data_ptr(), eps, out.data_ptr(), rows, cols,
-                                _lib.stream_ptr()), "zk_layernorm_bf16")
+    fmt = _lib.FMT_F16 if dtype == torch.float16 else _lib.FMT_BF16
+    out = torch.empty((rows, planes * cols), dtype=dtype, device=x.device)
+    check(lib.zk_layernorm16(x.data_ptr(), _cuda(w, torch.float32, "w").data_ptr(),
+                             _cuda(b, torch.float32, "b").data_ptr(), eps, out.data_ptr(), rows, cols, fmt, planes,
+                             _lib.stream_ptr()), "zk_layernorm16")
     return out
 
 
 def attention(qkv: torch.Tensor, batch: int, tokens: int) -> torch.Tensor:
     lib = _lib.load()
-    qkv = _cuda(qkv, torch.bfloat16, "attention qkv")
+    fmt = _fmt_of(qkv, "attention qkv")
+    qkv = _cuda(qkv, _DT[fmt], "attention qkv")
     if qkv.shape != (batch * tokens, 3 * HID):
         raise ZkError(f"attention: qkv must be ({batch * tokens}, {3 * HID}), got {tuple(qkv.shape)}")
-    out = torch.empty((batch * tokens, HID), dtype=torch.bfloat16, device=qkv.device)
-    check(lib.zk_attention_bf16(qkv.data_ptr(), out.data_ptr(), batch, tokens, _lib.stream_ptr()), "zk_attention_bf16")
+    out = torch.empty((batch * tokens, HID), dtype=_DT[fmt], device=qkv.device)
+    check(lib.zk_attention16(qkv.data_ptr(), out.data_ptr(), batch, tokens, fmt, _lib.stream_ptr()), "zk_attention16")
+    return out
+
+
+def attention_split(qkv: torch.Tensor, batch: int, tokens: int) -> torch.Tensor:
+    """Re-check precision: ``qkv`` fp16 (batch*tokens, 2*2304) hi | lo planes -> fp16 (batch*tokens, 2*768) hi | lo."""
+    lib = _lib.load()
+    qkv = _cuda(qkv, torch.float16, "attention_split qkv")
+    if qkv.shape != (batch * tokens, 6 * HID):
+        raise ZkError(f"attention_split: qkv must be ({batch * tokens}, {6 * HID}), got {tuple(qkv.shape)}")
+    out = torch.empty((batch * tokens, 2 * HID), dtype=torch.float16, device=qkv.device)
+    check(lib.zk_attention_split(qkv.data_ptr(), out.data_ptr(), batch, tokens, _lib.stream_ptr()), "zk_attention_split")
     return out
 
 
@@ -226,15 +271,53 @@ def gate_compact(logits: torch.Tensor, threshold: float, min_prob: Optional[floa
     return probs, pred, index, count
 
 
+def band_select(logits: torch.Tensor, margins, eps: float, src_window: Optional[torch.Tensor] = None):
+    """Rows whose margin ``l1 - l0`` is within ``eps`` of one of ``margins`` (<= 4 decision points, logit units).
+    Returns ``(pos (n,) i32, window (n,) i32, count (1,) i32)`` on the device; the first ``count`` entries are valid,
+    ascending.  ``window[j] = src_window[pos[j]]`` when a compacted index list is given, else ``pos[j]``."""
+    lib = _lib.load()
+    logits = _cuda(logits, torch.float32, "band_select")
+    n = logits.shape[0]
+    dev = logits.device
+    pos = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    window = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    mg = (C.c_float * 4)(*([float(m) for m in margins] + [0.0] * (4 - len(margins))))
+    check(lib.zk_band_select(logits.data_ptr(), n, mg, len(margins), float(eps),
+                             src_window.data_ptr() if src_window is not None else None, pos.data_ptr(),
+                             window.data_ptr(), count.data_ptr(), _lib.stream_ptr()), "zk_band_select")
+    return pos, window, count
+
+
+def scatter_rows2(src: torch.Tensor, pos: torch.Tensor, count: int, dst: torch.Tensor) -> None:
+    """``dst[pos[j]] = src[j]`` for ``j < count`` (rows of two fp32 values)."""
+    lib = _lib.load()
+    check(lib.zk_scatter_rows2(_cuda(src, torch.float32, "scatter src").data_ptr(), pos.data_ptr(), int(count),
+                               dst.data_ptr(), _lib.stream_ptr()), "zk_scatter_rows2")
+
+
 # ------------------------------------------------------------------------------------------ model
 PFX = "audio_spectrogram_transformer."
+_FORMATS = {"fp16": _lib.FMT_F16, "f16": _lib.FMT_F16, "float16": _lib.FMT_F16, "bf16": _lib.FMT_BF16,
+            "bfloat16": _lib.FMT_BF16}
+
+
+def default_operand_format() -> str:
+    """fp16 unless ``ZK_OPERANDS=bf16``: tcgen05 kind::f16 runs both at the same rate, fp16 keeps 3 more bits."""
+    import os
+
+    v = os.environ.get("ZK_OPERANDS", "fp16").lower()
+    if v not in _FORMATS:
+        raise ZkError(f"ZK_OPERANDS={v!r}: expected fp16 or bf16")
+    return v
 
 
 class AstModel:
-    """Owns a ``zk_model`` (packed bf16 weights on the device) and a reusable activation workspace."""
+    """Owns a ``zk_model`` (packed 16-bit weights on the device) and a reusable activation workspace."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], max_length: int = 1024, num_labels: int = 2,
-                 ln_eps: float = 1e-12, num_layers: int = 12, device: Optional[torch.device] = None):
+                 ln_eps: float = 1e-12, num_layers: int = 12, device: Optional[torch.device] = None,
+                 operand_format: Optional[str] = None):
         lib = _lib.load()
         _lib.require_device()
         self._lib = lib
@@ -251,6 +334,10 @@ class AstModel:
 
         w = _lib.AstWeights()
         w.num_layers, w.max_length, w.num_labels, w.ln_eps = num_layers, max_length, num_labels, ln_eps
+        self.operand_format = (operand_format or default_operand_format()).lower()
+        if self.operand_format not in _FORMATS:
+            raise ZkError(f"operand_format {operand_format!r}: expected 'fp16' or 'bf16'")
+        w.operand_format = _FORMATS[self.operand_format]
         e = PFX + "embeddings."
         w.cls_token, w.dist_token, w.pos_emb = p(e + "cls_token"), p(e + "distillation_token"), p(e + "position_embeddings")
         w.patch_w, w.patch_b = p(e + "patch_embeddings.projection.weight"), p(e + "patch_embeddings.projection.bias")
@@ -287,41 +374,57 @@ class AstModel:
             self._lib.zk_model_destroy(h)
             self._h = None
 
-    def workspace_bytes(self, batch: int) -> int:
-        return int(self._lib.zk_model_workspace_bytes(self._h, batch))
+    def workspace_bytes(self, batch: int, precision: int = _lib.PRECISION_FAST) -> int:
+        return int(self._lib.zk_model_workspace_bytes(self._h, batch, precision))
 
-    def _workspace(self, batch: int) -> torch.Tensor:
-        need = self.workspace_bytes(batch)
+    def _workspace(self, batch: int, precision: int = _lib.PRECISION_FAST) -> torch.Tensor:
+        need = self.workspace_bytes(batch, precision)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward_features(self, feats: torch.Tensor, return_hidden: bool = False):
-        """(B, max_length, 128) normalised features (CUDA fp32) -> logits (B, num_labels) fp32."""
+    def forward_features(self, feats: torch.Tensor, return_hidden: bool = False, precision: int = _lib.PRECISION_FAST,
+                         row_index: Optional[torch.Tensor] = None, batch: Optional[int] = None):
+        """(B, max_length, 128) normalised features (CUDA fp32) -> logits (B, num_labels) fp32.  With ``row_index``
+        (CUDA int32) window ``i`` of the ``batch`` reads ``feats[row_index[i]]``."""
         f = _cuda(feats, torch.float32, "forward_features")
         if f.dim() != 3 or f.shape[1] != self.max_length or f.shape[2] != 128:
             raise ZkError(f"forward_features: expected (B, {self.max_length}, 128), got {tuple(f.shape)}")
-        b = f.shape[0]
+        b = f.shape[0] if row_index is None else int(batch if batch is not None else row_index.numel())
         logits = torch.empty((b, self.num_labels), dtype=torch.float32, device=f.device)
         hidden = torch.empty((b, self.tokens, HID), dtype=torch.float32, device=f.device) if return_hidden else None
         if b:
-            ws = self._workspace(b)
-            check(self._lib.zk_model_forward(self._h, f.data_ptr(), b, ws.data_ptr(), ws.numel(), logits.data_ptr(),
+            ws = self._workspace(b, precision)
+            check(self._lib.zk_model_forward(self._h, f.data_ptr(), row_index.data_ptr() if row_index is not None else None,
+                                             b, precision, ws.data_ptr(), ws.numel(), logits.data_ptr(),
                                              hidden.data_ptr() if hidden is not None else None, _lib.stream_ptr()),
                   "zk_model_forward")
         return (logits, hidden) if return_hidden else logits
 
+    def recheck_features(self, feats: torch.Tensor, logits: torch.Tensor, margins, eps: float, chunk: int = 16) -> int:
+        """Decision re-check on the contract path: rows of ``logits`` whose margin is within ``eps`` of a decision point
+        are recomputed at ``PRECISION_RECHECK`` from the same feature rows and overwritten in place.  Returns how many."""
+        if eps <= 0 or not len(margins) or logits.shape[0] == 0:
+            return 0
+        pos, _, count = band_select(logits, margins, eps)
+        r = int(count.item())
+        for base in range(0, r, chunk):
+            n = min(chunk, r - base)
+            hi = self.forward_features(feats, precision=_lib.PRECISION_RECHECK, row_index=pos[base:base + n], batch=n)
+            scatter_rows2(hi, pos[base:base + n], n, logits)
+        return r
+
     def forward_fbank(self, fbank: torch.Tensor, batch: int, mean: float, std: float, window_base: int = 0,
                       window_index: Optional[torch.Tensor] = None, frames_per_hop: int = 50, valid_frames: int = 98,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, precision: int = _lib.PRECISION_FAST) -> torch.Tensor:
         """Fused path: windows are gathered from the compact continuous fbank ``(m,128)`` (un-normalised)."""
         fb = _cuda(fbank, torch.float32, "forward_fbank")
         logits = out if out is not None else torch.empty((batch, self.num_labels), dtype=torch.float32, device=fb.device)
         if batch:
-            ws = self._workspace(batch)
+            ws = self._workspace(batch, precision)
             check(self._lib.zk_model_forward_fbank(
                 self._h, fb.data_ptr(), fb.shape[0], window_index.data_ptr() if window_index is not None else None,
-                window_base, frames_per_hop, valid_frames, float(mean), float(std), batch, ws.data_ptr(), ws.numel(),
-                logits.data_ptr(), _lib.stream_ptr()), "zk_model_forward_fbank")
+                window_base, frames_per_hop, valid_frames, float(mean), float(std), batch, precision, ws.data_ptr(),
+                ws.numel(), logits.data_ptr(), _lib.stream_ptr()), "zk_model_forward_fbank")
         return logits

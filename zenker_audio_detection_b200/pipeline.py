@@ -4,8 +4,11 @@
       -> H2D -> channel mean + polyphase resample to 16 kHz           (zk_resample_*)
       -> ONE continuous Kaldi fbank over the whole recording            (zk_fbank_f32)        SURVEY.md 0.9
       -> Stage 1: batches of windows gathered straight from the compact fbank (frame = 50 w + t), AST forward
+      -> decision re-check: windows whose margin is within eps of a threshold are re-run at fp32-class precision
+         (zk_band_select -> zk_model_forward_fbank(ZK_PRECISION_RECHECK) -> zk_scatter_rows2), so that ...
       -> softmax + threshold gate + order-preserving compaction         (zk_gate_compact)
-      -> Stage 2: AST forward on the compacted window index list (same fbank, Stage-2 normalisation)
+         ... decides exactly as the reference's fp32 gate does (ref:312-320)
+      -> Stage 2: AST forward on the compacted window index list (same fbank, Stage-2 normalisation) + re-check
       -> one D2H of the per-window scores; summary / aggregation on the host (cascade.py)
 
 The (B,1024,128) feature tensor of the reference (512 KiB per window, 90 % constant padding) is never
@@ -20,10 +23,10 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import cascade, ops
+from . import _lib, cascade, ops
 from ._lib import ZkError
 from .fx import ZenkerASTFeatureExtractor
-from .model import ZenkerASTForAudioClassification
+from .model import ZenkerASTForAudioClassification, decision_margins, default_recheck_eps
 
 SAMPLING_RATE = 16000
 FRAME_SHIFT = 160
@@ -38,6 +41,8 @@ class RecordingResult:
     s2_probs: np.ndarray          # (K,2) float32
     classes: np.ndarray           # (N,) -1 idle / 0 healthy / 1 zenker
     summary: Dict[str, Any] = field(default_factory=dict)
+    rechecked_s1: int = 0         # windows re-run at PRECISION_RECHECK before the Stage-1 gate
+    rechecked_s2: int = 0         # forwarded windows re-run before the Stage-2 decision
 
     @property
     def stage2_results(self):
@@ -49,7 +54,8 @@ class TwoStagePipeline:
                  model_s2: ZenkerASTForAudioClassification, fx_s2: ZenkerASTFeatureExtractor, batch_size: int = 128,
                  window_sec: float = 1.0, hop_sec: float = 0.5, stage1_threshold: float = 0.5,
                  stage2_threshold: float = 0.5, stage1_forward_min_prob: Optional[float] = None,
-                 stage2_argmax: bool = False, device: Optional[Union[str, torch.device]] = None):
+                 stage2_argmax: bool = False, device: Optional[Union[str, torch.device]] = None,
+                 recheck_eps: Optional[float] = None, recheck_batch: int = 16):
         if not torch.cuda.is_available():
             raise ZkError("TwoStagePipeline needs a B200; there is no CPU path")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -60,6 +66,17 @@ class TwoStagePipeline:
         self.thr1, self.thr2 = float(stage1_threshold), float(stage2_threshold)
         self.min_prob = stage1_forward_min_prob
         self.stage2_argmax = bool(stage2_argmax)
+        # decision re-check (module docstring): every threshold the reference applies to a stage's scores is a decision
+        # point -- Stage 1: argmax (ref:313, and the bare argmax of summarize, ref:156), p1 >= thr1 (ref:316), the cached
+        # script's forward_min_prob (refc:471-478); Stage 2: p_zenker >= thr2 (ref:333) or argmax (refc:512-515)
+        self.recheck_eps = float(recheck_eps) if recheck_eps is not None else max(
+            default_recheck_eps(self.m1.operand_format), default_recheck_eps(self.m2.operand_format))
+        self.recheck_batch = int(recheck_batch)
+        thr_s1, thr_s2 = [0.5, self.thr1, self.min_prob], [0.5 if self.stage2_argmax else self.thr2]
+        self.margins1, self.margins2 = decision_margins(thr_s1), decision_margins(thr_s2)
+        # the drop-in __call__ of the two models (cached flow, cache.py) re-checks against the same decision points
+        self.m1.recheck_thresholds, self.m1.recheck_eps = thr_s1, self.recheck_eps
+        self.m2.recheck_thresholds, self.m2.recheck_eps = thr_s2, self.recheck_eps
         for fx in (fx_s1, fx_s2):
             if fx.sampling_rate != SAMPLING_RATE:
                 raise ZkError("the two-stage path runs at 16 kHz (ref:47)")
@@ -70,31 +87,46 @@ class TwoStagePipeline:
         self.fused = (same_geometry and self.hop % FRAME_SHIFT == 0 and fx_s1.do_normalize
                       and fx_s1.num_mel_bins == 128 and self.m1.max_length == fx_s1.max_length == self.m2.max_length)
         self.valid_frames = min(ops.FbankPlan.num_frames(self.win), fx_s1.max_length)
-        self.plan = fx_s1._get_plan()
+        self.plan = fx_s1._get_plan(self.device)
 
     # ------------------------------------------------------------------ stages
     def _stage_logits(self, model: ZenkerASTForAudioClassification, fx: ZenkerASTFeatureExtractor, audio: torch.Tensor,
-                      fbank: Optional[torch.Tensor], n: int, index: Optional[torch.Tensor]) -> torch.Tensor:
+                      fbank: Optional[torch.Tensor], n: int, index: Optional[torch.Tensor],
+                      precision: int = _lib.PRECISION_FAST, batch_size: Optional[int] = None) -> torch.Tensor:
         """Logits (n,2) for windows ``index[:n]`` (or 0..n-1 when index is None)."""
         eng = model.engine
         out = torch.empty((n, model.num_labels), dtype=torch.float32, device=self.device)
-        B = self.batch_size
+        B = batch_size or self.batch_size
         for base in range(0, n, B):
             b = min(B, n - base)
             if self.fused:
                 eng.forward_fbank(fbank, b, fx.mean, fx.std, window_base=base,
                                   window_index=None if index is None else index[base:base + b],
                                   frames_per_hop=self.hop // FRAME_SHIFT, valid_frames=self.valid_frames,
-                                  out=out[base:base + b])
+                                  out=out[base:base + b], precision=precision)
             else:
                 if index is None:
                     starts = torch.arange(base, base + b, device=self.device, dtype=torch.int64) * self.hop
                 else:
                     starts = index[base:base + b].to(torch.int64) * self.hop
                 wins = audio[(starts.unsqueeze(1) + torch.arange(self.win, device=self.device)).reshape(-1)].view(b, self.win)
-                feats = fx._get_plan().fx_contract(wins, fx.mean, fx.std, fx.max_length, fx.do_normalize)
-                out[base:base + b] = eng.forward_features(feats)
+                feats = fx._get_plan(self.device).fx_contract(wins, fx.mean, fx.std, fx.max_length, fx.do_normalize)
+                out[base:base + b] = eng.forward_features(feats, precision=precision)
         return out
+
+    def _recheck(self, model, fx, audio, fbank, logits: torch.Tensor, index: Optional[torch.Tensor], margins) -> int:
+        """Re-run the windows of ``logits`` (rows = windows ``index[:n]`` or 0..n-1) that sit within ``recheck_eps`` of a
+        decision point at PRECISION_RECHECK and overwrite their rows.  One synchronisation (the count)."""
+        n = logits.shape[0]
+        if self.recheck_eps <= 0 or not margins or n == 0 or model.num_labels != 2:
+            return 0
+        pos, window, count = ops.band_select(logits, margins, self.recheck_eps, index)
+        r = int(count.item())
+        if r:
+            hi = self._stage_logits(model, fx, audio, fbank, r, window, precision=_lib.PRECISION_RECHECK,
+                                    batch_size=self.recheck_batch)
+            ops.scatter_rows2(hi, pos, r, logits)
+        return r
 
     def run_audio16k(self, audio: torch.Tensor) -> RecordingResult:
         """``audio``: CUDA float32 mono 16 kHz (what ``load_audio`` returns, ref:53-59)."""
@@ -107,12 +139,15 @@ class TwoStagePipeline:
             logits1 = self._stage_logits(self.m1, self.fx1, audio, fbank, n, None)
             if logits1.dim() != 2 or logits1.shape[1] != 2:
                 raise RuntimeError("Stage1 output shape unexpected; expected (N,2)")  # ref:310-311
+            re1 = self._recheck(self.m1, self.fx1, audio, fbank, logits1, None, self.margins1)
             probs1, pred, index, count = ops.gate_compact(logits1, self.thr1, self.min_prob)
-            k = int(count.item())  # the only mid-pipeline synchronisation: Stage 2's batch count depends on it
+            k = int(count.item())  # Stage 2's batch count depends on it
+            re2 = 0
             if k:
                 logits2 = self._stage_logits(self.m2, self.fx2, audio, fbank, k, index)
                 if logits2.shape[1] != 2:
                     raise RuntimeError("Stage2 output shape unexpected; expected (K,2)")  # ref:325-326
+                re2 = self._recheck(self.m2, self.fx2, audio, fbank, logits2, index, self.margins2)
                 probs2 = ops.softmax2(logits2)
             else:
                 probs2 = torch.zeros((0, 2), dtype=torch.float32, device=self.device)
@@ -122,7 +157,7 @@ class TwoStagePipeline:
             s2 = probs2.cpu().numpy()
         classes = cascade.stage2_classes(n, idx, s2, self.thr2, self.stage2_argmax)
         summary = cascade.summarize_stage_outputs(s1, idx, s2, self.thr2, self.stage2_argmax)
-        return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary)
+        return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary, re1, re2)
 
     def resample_to_device(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> torch.Tensor:
         """ref:53-59 (``load_audio`` after the decode): H2D, channel mean, resample -> CUDA float32 mono 16 kHz."""
