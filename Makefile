@@ -4,7 +4,7 @@ CSRC      := zenker_audio_detection_b200/csrc
 LIBDIR    := zenker_audio_detection_b200/lib
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC) \
              --expt-relaxed-constexpr -Xptxas -v
-SRCS      := $(CSRC)/zk_host.cu $(CSRC)/zk_gemm.cu $(CSRC)/zk_attn.cu $(CSRC)/zk_attn_split.cu $(CSRC)/zk_ops.cu $(CSRC)/zk_frontend.cu $(CSRC)/zk_model.cu
+SRCS      := $(CSRC)/zk_host.cu $(CSRC)/zk_gemm.cu $(CSRC)/zk_attn.cu $(CSRC)/zk_attn_split.cu $(CSRC)/zk_ops.cu $(CSRC)/zk_frontend.cu $(CSRC)/zk_model.cu $(CSRC)/zk_cascade.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 HDRS      := include/zk_b200.h $(wildcard $(CSRC)/*.cuh)
 

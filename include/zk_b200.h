@@ -143,6 +143,7 @@ typedef struct zk_model zk_model;
 int zk_model_create(const zk_ast_weights* w, zk_model** out);
 void zk_model_destroy(zk_model* m);
 int zk_model_num_tokens(const zk_model* m);
+int zk_model_max_length(const zk_model* m);
 /* bytes of caller-provided workspace zk_model_forward* needs for `batch` windows at `precision` */
 size_t zk_model_workspace_bytes(const zk_model* m, int batch, int precision);
 
@@ -185,6 +186,41 @@ int zk_scatter_rows2(const float* d_src, const int32_t* d_pos, int count, float*
  * sum(x^2) over n floats, accumulated in float64 (the caller zeroes d_acc before the first batch; zero-padded feature
  * rows simply add 0, so the continuous or the padded layout give the same sums). */
 int zk_sum_sumsq_f64(const float* d_x, int64_t n, double* d_acc, zk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (6) The whole cascade of one recording in ONE call -- replaces the per-recording body of ref:301-348 / refc:433-531
+ *     (SURVEY.md section 8b "cascade_run"): continuous fbank, Stage 1 in batches, decision re-check, gate + compaction,
+ *     Stage 2 on the compacted windows, re-check, softmax.  A C host drives the path with zk_resample_* + this.
+ *       d_audio16k  [n_samples] f32 mono 16 kHz, n_samples >= window_samples (zero-pad a shorter recording, ref:70-73)
+ *       outputs     d_probs1 [N][2] f32, d_pred1 [N] i32, d_index [N] i32 (first num_forwarded valid, ascending),
+ *                   d_probs2 [N][2] f32 (row j belongs to window d_index[j]);  N = (n_samples - window) / hop + 1
+ *       h_counts    HOST: N, forwarded count, how many windows each stage re-ran at ZK_PRECISION_RECHECK
+ *     hop_samples must be a multiple of 160 (the fused gather; otherwise use the per-window entry points).
+ *     SYNCHRONISATION: the batch counts of later steps are produced on the device, so this entry point -- unlike every
+ *     other one -- synchronises `stream` up to four times (band count x 2, gate count) before it returns; all kernels
+ *     are still enqueued on `stream`, and the outputs are complete only after the caller synchronises it once more.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zk_cascade_params {
+  int32_t batch_size;      /* windows per launch of the FAST forward (128) */
+  int32_t recheck_batch;   /* windows per launch of the RECHECK forward (16) */
+  int32_t window_samples;  /* int(window_sec * 16000), ref:63 */
+  int32_t hop_samples;     /* int(hop_sec * 16000), ref:64 */
+  float mean1, std1;       /* Stage-1 extractor statistics (HF:feature_extraction...:155-156) */
+  float mean2, std2;       /* Stage-2 */
+  float thr1;              /* ref:316 */
+  float min_prob;          /* refc:471-478; < 0 = none */
+  float thr2;              /* ref:333 */
+  int32_t stage2_argmax;   /* refc:512-515 */
+  float recheck_eps;       /* half-width (logit units) of the re-check band; 0 disables the re-check */
+} zk_cascade_params;
+typedef struct zk_cascade_counts {
+  int32_t num_windows, num_forwarded, rechecked_s1, rechecked_s2;
+} zk_cascade_counts;
+/* 0 on bad arguments */
+size_t zk_cascade_workspace_bytes(const zk_model* m1, const zk_model* m2, int64_t n_samples, const zk_cascade_params* p);
+int zk_cascade_run(const zk_fbank_plan* plan, zk_model* m1, zk_model* m2, const float* d_audio16k, int64_t n_samples,
+                   const zk_cascade_params* p, void* d_workspace, size_t workspace_bytes, float* d_probs1, int32_t* d_pred1,
+                   int32_t* d_index, float* d_probs2, zk_cascade_counts* h_counts, zk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks, exported so the parity tests can pin each kernel separately.

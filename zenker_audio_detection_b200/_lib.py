@@ -48,6 +48,18 @@ class AstWeights(C.Structure):
     ]
 
 
+class CascadeParams(C.Structure):
+    _fields_ = [("batch_size", C.c_int32), ("recheck_batch", C.c_int32), ("window_samples", C.c_int32),
+                ("hop_samples", C.c_int32), ("mean1", C.c_float), ("std1", C.c_float), ("mean2", C.c_float),
+                ("std2", C.c_float), ("thr1", C.c_float), ("min_prob", C.c_float), ("thr2", C.c_float),
+                ("stage2_argmax", C.c_int32), ("recheck_eps", C.c_float)]
+
+
+class CascadeCounts(C.Structure):
+    _fields_ = [("num_windows", C.c_int32), ("num_forwarded", C.c_int32), ("rechecked_s1", C.c_int32),
+                ("rechecked_s2", C.c_int32)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header is exported
 SIGNATURES = {
     "zk_abi_version": (C.c_int, []),
@@ -66,6 +78,7 @@ SIGNATURES = {
     "zk_model_create": (C.c_int, [C.POINTER(AstWeights), C.POINTER(C.c_void_p)]),
     "zk_model_destroy": (None, [C.c_void_p]),
     "zk_model_num_tokens": (C.c_int, [C.c_void_p]),
+    "zk_model_max_length": (C.c_int, [C.c_void_p]),
     "zk_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "zk_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -78,6 +91,10 @@ SIGNATURES = {
     "zk_band_select": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "zk_scatter_rows2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "zk_cascade_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(CascadeParams)]),
+    "zk_cascade_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(CascadeParams),
+                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(CascadeCounts), C.c_void_p]),
     "zk_sum_sumsq_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zk_gemm16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),

@@ -1,8 +1,9 @@
 // Attention at re-check precision: O = softmax(Q K^T / 8) V per (window, head) with every operand carried as two
 // fp16 planes (x = hi + lo, 22 significant bits) and both contractions evaluated as three-product sums
 //     Q K^T = Q_lo K_hi^T + Q_hi K_lo^T + Q_hi K_hi^T          P V = P_lo V_hi + P_hi V_lo + P_hi V_hi
-// with fp32 accumulation, an fp32 online softmax against the TRUE running maximum and exp2f (no polynomial, no stale
-// maximum): the result is within a few 2^-22 of an fp32 evaluation (HF:modeling_audio_spectrogram_transformer.py:
+// with fp32 accumulation (short tensor-core chains joined by rounded fp32 adds, because the tensor core truncates), an
+// fp32 online softmax against the TRUE running maximum and exp2f (no polynomial, no stale maximum): the result is
+// within a few 2^-22 of an fp32 evaluation (HF:modeling_audio_spectrogram_transformer.py:
 // 162-176 on the CPU), which is what the decision re-check needs.
 //
 // This kernel only ever sees the few windows whose fast logits are within eps of a threshold, so it is built for
@@ -56,7 +57,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(THREADS) attn_split_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+__global__ void __launch_bounds__(THREADS, 3) attn_split_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                                                              int tokens) {
   extern __shared__ __align__(16) __half sm[];
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -121,24 +122,31 @@ __global__ void __launch_bounds__(THREADS) attn_split_kernel(const __half* __res
     const uint32_t k_hi = smem_u32(st), k_lo = smem_u32(st + TILE_H), v_hi = smem_u32(st + 2 * TILE_H),
                    v_lo = smem_u32(st + 3 * TILE_H);
 
-    // ---- S = Q K^T (16 x 64 per warp), three products, smallest terms first per k-step
+    // ---- S = Q K^T (16 x 64 per warp).  The tensor core TRUNCATES when it adds into its accumulator (probed:
+    // scripts/accum_probe.py), i.e. every mma step costs up to one ulp of the accumulator, always towards zero.  So the
+    // large products (hi x hi) get a chain of their own that is as short as possible (4 steps) and the two small
+    // products, 2^-11 of the result, another one; the chains are joined by an ordinary rounded fp32 add.
     float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key n-tiles
+      float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f}, l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key n-tiles
+      for (int kk = 0; kk < 4; ++kk) {
         uint32_t bh[4], bl[4];
         const uint32_t off = (uint32_t)((jp * 16 * ROW_H + kk * 16 + k_off) * 2);
         ldsm_x4(k_hi + off, bh);
         ldsm_x4(k_lo + off, bl);
-        mma16816(s[2 * jp], qf[1][kk], bh[0], bh[1]);      // Q_lo K_hi
-        mma16816(s[2 * jp], qf[0][kk], bl[0], bl[1]);      // Q_hi K_lo
-        mma16816(s[2 * jp], qf[0][kk], bh[0], bh[1]);      // Q_hi K_hi
-        mma16816(s[2 * jp + 1], qf[1][kk], bh[2], bh[3]);
-        mma16816(s[2 * jp + 1], qf[0][kk], bl[2], bl[3]);
-        mma16816(s[2 * jp + 1], qf[0][kk], bh[2], bh[3]);
+        mma16816(l0, qf[1][kk], bh[0], bh[1]);      // Q_lo K_hi
+        mma16816(l0, qf[0][kk], bl[0], bl[1]);      // Q_hi K_lo
+        mma16816(h0, qf[0][kk], bh[0], bh[1]);      // Q_hi K_hi
+        mma16816(l1, qf[1][kk], bh[2], bh[3]);
+        mma16816(l1, qf[0][kk], bl[2], bl[3]);
+        mma16816(h1, qf[0][kk], bh[2], bh[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[2 * jp][e] = h0[e] + l0[e];
+        s[2 * jp + 1][e] = h1[e] + l1[e];
       }
     }
 
@@ -183,26 +191,37 @@ __global__ void __launch_bounds__(THREADS) attn_split_kernel(const __half* __res
       l_b += s[i][2] + s[i][3];
     }
 
-    // ---- O += P V: the accumulator layout of two adjacent n-tiles IS the A-fragment layout of one 16-key k-step
+    // ---- O += P V: the accumulator layout of two adjacent n-tiles IS the A-fragment layout of one 16-key k-step.
+    // Per key block the product is formed in fresh short chains (see above) and added to the running O with a rounded
+    // fp32 add: accumulating all 19 blocks inside the tensor core would be a 228-step truncating chain (~1e-5).
+    uint32_t ph[4][4], pl[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      uint32_t ph[4], pl[4];
-      split_f16_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);          // row g,     keys 16 kk + 2t, +1
-      split_f16_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);          // row g + 8
-      split_f16_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);  // row g,     keys 16 kk + 8 + 2t, +1
-      split_f16_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);  // row g + 8
+      split_f16_pair(s[2 * kk][0], s[2 * kk][1], ph[kk][0], pl[kk][0]);          // row g,     keys 16 kk + 2t, +1
+      split_f16_pair(s[2 * kk][2], s[2 * kk][3], ph[kk][1], pl[kk][1]);          // row g + 8
+      split_f16_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[kk][2], pl[kk][2]);  // row g,     keys 16 kk + 8 + 2t, +1
+      split_f16_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[kk][3], pl[kk][3]);  // row g + 8
+    }
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-dim n-tiles
+    for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-dim n-tiles
+      float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f}, l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
         uint32_t bh[4], bl[4];
         const uint32_t off = (uint32_t)((kk * 16 * ROW_H + jp * 16 + v_off) * 2);
         ldsm_x4_trans(v_hi + off, bh);
         ldsm_x4_trans(v_lo + off, bl);
-        mma16816(o[2 * jp], pl, bh[0], bh[1]);      // P_lo V_hi
-        mma16816(o[2 * jp], ph, bl[0], bl[1]);      // P_hi V_lo
-        mma16816(o[2 * jp], ph, bh[0], bh[1]);      // P_hi V_hi
-        mma16816(o[2 * jp + 1], pl, bh[2], bh[3]);
-        mma16816(o[2 * jp + 1], ph, bl[2], bl[3]);
-        mma16816(o[2 * jp + 1], ph, bh[2], bh[3]);
+        mma16816(l0, pl[kk], bh[0], bh[1]);      // P_lo V_hi
+        mma16816(l0, ph[kk], bl[0], bl[1]);      // P_hi V_lo
+        mma16816(h0, ph[kk], bh[0], bh[1]);      // P_hi V_hi
+        mma16816(l1, pl[kk], bh[2], bh[3]);
+        mma16816(l1, ph[kk], bl[2], bl[3]);
+        mma16816(h1, ph[kk], bh[2], bh[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[2 * jp][e] += h0[e] + l0[e];
+        o[2 * jp + 1][e] += h1[e] + l1[e];
       }
     }
     __syncthreads();  // everyone is done with stage (j & 1) before the next iteration's prefetch overwrites it

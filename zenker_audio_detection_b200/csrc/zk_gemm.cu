@@ -49,6 +49,7 @@ struct Params {
   int a_off[MAX_PRODUCTS];     // column (element) offset of the A plane of product i
   int w_off[MAX_PRODUCTS];     // same for W
   int out_plane_stride;        // ..._SPLIT epilogues: columns between the hi and lo output planes (= N)
+  int seg_kb;                  // SEG kernels: k-blocks per accumulator chain
 };
 
 // PATCH epilogue only: one thread owns 32 consecutive columns [col0, col0+32) of row `row`; rows are scattered to
@@ -138,14 +139,33 @@ __device__ __forceinline__ void bias_act_split(const uint32_t (&r)[32], const fl
 
 constexpr bool epi_is_split(int epi) { return epi == ZK_EPI_BIAS_SPLIT || epi == ZK_EPI_BIAS_GELU_SPLIT; }
 
+// Segmented accumulation (SEG kernels: the split-operand residual GEMMs, K = 768 / 3072).  The tensor core TRUNCATES on
+// every accumulate -- one ulp of the accumulator per tcgen05.mma step, always towards zero; scripts/accum_probe.py
+// measures a relative shrink of -4e-6 after the 48 steps of K = 768 and -1.8e-5 after the 192 of K = 3072 on
+// same-signed data (torch's fp32 FFMA matmul: 1e-9) -- so a long K chain is cut into segments of SEG_KB k-blocks: 16
+// hi x hi steps, preceded by the 32 steps of the two small products while the accumulator is still ~2^-11 of its final
+// size.  Every segment is its own accumulator use (the two TMEM buffers alternate between segments) and its own
+// epilogue pass, joined to the others by the rounded fp32 add of the TMA reduce into the residual stream.
+// K = 768 runs 3 segments of 4 k-blocks; K = 3072 runs 6 of 8 (32 hi x hi steps: every segment is another 128 KiB
+// reduce-add per CTA into L2, and at 12 segments that traffic, not the tensor pipe, set the pace: 0.31 against 0.22 ms).
+// Measured against float64 (tests/test_gpu_gemm.py): rms error 0.4-0.7x that of torch's fp32 matmul.
+constexpr int SEG_KB = 4, SEG_KB_LONG = 8, SEG_LONG_K = 2048;
+
 // Epilogue of one accumulator tile for one warp (32 rows x 128 columns at t_acc), shared by the single-CTA and the
 // CTA-pair kernels: TMEM -> registers -> fused scale / bias / GELU -> 128B-swizzled staging tile -> TMA store (16-bit
 // outputs, one or two planes) or TMA reduce-add into the fp32 residual stream.
 template <int EPI, int FMT>
 __device__ __forceinline__ void epilogue_rows(const Params& p, const CUtensorMap* tmC, uint8_t* stg, uint32_t stg_row,
-                                              uint32_t t_acc, int row0, int col_base, int lane) {
+                                              uint32_t t_acc, int row0, int col_base, int lane, int seg = 0) {
   if constexpr (EPI == ZK_EPI_BIAS_RESID_F32) {
-    // 4 chunks of 32 fp32 columns: (acc * scale + bias) -> staging -> TMA reduce-add into the residual stream
+    // 4 chunks of 32 fp32 columns: (acc * scale + bias) -> staging -> TMA reduce-add into the residual stream.
+    // Segmented chains (SEG kernels): every segment is reduce-added on its own (a rounded fp32 add in L2), the bias goes
+    // with the first; this warp's previous segment must have LANDED before the next one is issued, so that the adds to an
+    // element always happen in the same order (bit-reproducible results).
+    if (seg > 0) {
+      if (lane == 0) bulk_wait0();
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t r[32];
@@ -156,7 +176,8 @@ __device__ __forceinline__ void epilogue_rows(const Params& p, const CUtensorMap
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 b = __ldg(bias4 + i);
+        float4 b = __ldg(bias4 + i);
+        if (seg > 0) b = make_float4(0.f, 0.f, 0.f, 0.f);
         st_shared_v4(stg_row + ((uint32_t)(i ^ (lane & 7)) << 4),
                      __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 0]), p.acc_scale, b.x)),
                      __float_as_uint(fmaf(__uint_as_float(r[i * 4 + 1]), p.acc_scale, b.y)),
@@ -232,10 +253,11 @@ __device__ __forceinline__ void epilogue_rows(const Params& p, const CUtensorMap
   }
 }
 
-template <int EPI, int FMT>
+template <int EPI, int FMT, bool SEG>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const Params p) {
+  static_assert(!SEG || EPI == ZK_EPI_BIAS_RESID_F32, "segments are joined by the reduce-add of the residual epilogue");
   constexpr uint32_t IDESC = umma_idesc_16(FMT, BM, BN, 0, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -270,7 +292,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.K / BK;
-  const int kblocks_all = kblocks * p.nprod;  // k-blocks the MMA warp consumes per tile (all products)
+  // accumulator chains per tile and k-blocks (all products) per chain
+  const int nseg = SEG ? kblocks / p.seg_kb : 1;
+  const int kb_per_seg = SEG ? p.seg_kb * p.nprod : kblocks * p.nprod;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -278,17 +302,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
-        for (int pr = 0; pr < p.nprod; ++pr) {
-          const int a0 = p.a_off[pr], w0 = p.w_off[pr];
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-            uint8_t* sa = smem + stage * STAGE_BYTES;
-            tma_load_2d(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * BM);
-            tma_load_2d(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
+        for (int seg = 0; seg < nseg; ++seg) {
+          const int kb0 = SEG ? seg * p.seg_kb : 0, kb1 = SEG ? kb0 + p.seg_kb : kblocks;
+          for (int pr = 0; pr < p.nprod; ++pr) {
+            const int a0 = p.a_off[pr], w0 = p.w_off[pr];
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+              uint8_t* sa = smem + stage * STAGE_BYTES;
+              tma_load_2d(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * BM);
+              tma_load_2d(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
         }
@@ -299,14 +326,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // `lane == 0` ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~90 clk per instruction).
     int stage = 0;
     uint32_t phase = 0;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    int t = 0;  // accumulator uses so far: one per tile, or one per segment of a tile
+    for (int u = blockIdx.x * nseg, uend = num_tiles * nseg; u < uend; u += ((u + 1) % nseg ? 1 : (gridDim.x - 1) * nseg + 1), ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < kblocks_all; ++kb) {
+      for (int kb = 0; kb < kb_per_seg; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -318,7 +345,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (kb == kblocks_all - 1) umma_commit(&tfull[acc]);
+          if (kb == kb_per_seg - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -333,7 +360,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES;  // this warp's 32 x 128 B staging tile (1024-B aligned)
     const uint32_t stg_row = smem_u32(stg) + lane * 128;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    for (int u = blockIdx.x * nseg, uend = num_tiles * nseg; u < uend; u += ((u + 1) % nseg ? 1 : (gridDim.x - 1) * nseg + 1), ++t) {
+      const int tile = u / nseg, seg = u - tile * nseg;
       const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
       const int acc = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
@@ -381,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
-        epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane);
+        epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane, seg);
       }
       tc_fence_before();
       __syncwarp();
@@ -461,11 +489,12 @@ __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
       : "memory");
 }
 
-template <int EPI, int FMT>
+template <int EPI, int FMT, bool SEG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
   static_assert(EPI != ZK_EPI_PATCH_F32, "the patch-embedding epilogue stays on the single-CTA kernel");
+  static_assert(!SEG || EPI == ZK_EPI_BIAS_RESID_F32, "segments are joined by the reduce-add of the residual epilogue");
   constexpr uint32_t IDESC2 = umma_idesc_16(FMT, 2 * BM, BN, 0, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -503,7 +532,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row tiles here
   const int kblocks = p.K / BK;
-  const int kblocks_all = kblocks * p.nprod;
+  const int nseg = SEG ? kblocks / p.seg_kb : 1;
+  const int kb_per_seg = SEG ? p.seg_kb * p.nprod : kblocks * p.nprod;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -512,17 +542,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
-        for (int pr = 0; pr < p.nprod; ++pr) {
-          const int a0 = p.a_off[pr], w0 = p.w_off[pr];
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);  // both CTAs' tiles land on this barrier
-            uint8_t* sa = smem + stage * STAGE2_BYTES;
-            tma_load_2d_pair(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * 2 * BM + (int)rank * BM);
-            tma_load_2d_pair(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN + (int)rank * 128);
-            if (++stage == STAGES2) {
-              stage = 0;
-              phase ^= 1;
+        for (int seg = 0; seg < nseg; ++seg) {
+          const int kb0 = SEG ? seg * p.seg_kb : 0, kb1 = SEG ? kb0 + p.seg_kb : kblocks;
+          for (int pr = 0; pr < p.nprod; ++pr) {
+            const int a0 = p.a_off[pr], w0 = p.w_off[pr];
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);  // both CTAs' tiles land on this barrier
+              uint8_t* sa = smem + stage * STAGE2_BYTES;
+              tma_load_2d_pair(sa, &tmA, &full[stage], a0 + kb * BK, m_blk * 2 * BM + (int)rank * BM);
+              tma_load_2d_pair(sa + A_BYTES, &tmB, &full[stage], w0 + kb * BK, n_blk * BN + (int)rank * 128);
+              if (++stage == STAGES2) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
         }
@@ -532,14 +565,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
-      int t = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      int t = 0;  // accumulator uses so far: one per tile, or one per segment of a tile
+      for (int u = cluster_id * nseg, uend = num_tiles * nseg; u < uend; u += ((u + 1) % nseg ? 1 : (num_clusters - 1) * nseg + 1), ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (t >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks_all; ++kb) {
+        for (int kb = 0; kb < kb_per_seg; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -549,7 +582,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC2, (kb | k) != 0);
             umma_commit_pair(&empty[stage]);
-            if (kb == kblocks_all - 1) umma_commit_pair(&tfull[acc]);
+            if (kb == kb_per_seg - 1) umma_commit_pair(&tfull[acc]);
           }
           __syncwarp();
           if (++stage == STAGES2) {
@@ -565,7 +598,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem + OFF_STG2 + (warp - 2) * STG_BYTES;  // this warp's 32 x 128 B staging tile (1024-B aligned)
     const uint32_t stg_row = smem_u32(stg) + lane * 128;
     int t = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+    for (int u = cluster_id * nseg, uend = num_tiles * nseg; u < uend; u += ((u + 1) % nseg ? 1 : (num_clusters - 1) * nseg + 1), ++t) {
+      const int tile = u / nseg, seg = u - tile * nseg;
       const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
       const int acc = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
@@ -574,7 +608,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
       const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
-      epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane);
+      epilogue_rows<EPI, FMT>(p, &tmC, stg, stg_row, t_acc, row0, col_base, lane, seg);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_leader(&tempty[acc]);
@@ -588,11 +622,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
-template <int EPI, int FMT>
+template <int EPI, int FMT, bool SEG = false>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                        cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI, FMT>), SMEM2_BYTES, &attr_done)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI, FMT, SEG>), SMEM2_BYTES, &attr_done)) return rc;
   // persistent grid = the number of CTA pairs the device can hold at once (a TPC with one usable SM cannot host a
   // pair, so this may be less than num_sms / 2); asked from the runtime once per device
   static int resident[64] = {0};
@@ -612,7 +646,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.attrs = &at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI, FMT>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI, FMT, SEG>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = num_sms() / 2;
     }
@@ -623,21 +657,21 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = tiles < cap ? tiles : cap;
   ProfScope prof(prof_cls, stream);
-  gemm_pair_kernel<EPI, FMT><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_pair_kernel<EPI, FMT, SEG><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_pair_kernel");
   return 0;
 }
 }  // namespace pair
 
-template <int EPI, int FMT>
+template <int EPI, int FMT, bool SEG = false>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                   cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<EPI, FMT>), SMEM_BYTES, &attr_done)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<EPI, FMT, SEG>), SMEM_BYTES, &attr_done)) return rc;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope prof(prof_cls, stream);
-  gemm_kernel<EPI, FMT><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_kernel<EPI, FMT, SEG><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }
@@ -732,6 +766,9 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
   // (0.586 against 0.606 ms at M = 155 392 on the same box).
   static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 2;
   const bool f16 = g.fmt == FMT_F16;
+  // split-operand residual GEMMs: cut the K chain into segments joined by rounded adds (see SEG_KB)
+  p.seg_kb = K >= SEG_LONG_K ? SEG_KB_LONG : SEG_KB;
+  const bool seg = g.products == 3 && epilogue == ZK_EPI_BIAS_RESID_F32 && K % (BK * p.seg_kb) == 0 && K > BK * p.seg_kb;
   if (use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2)) {
     if ((rc = make_tmap_bf16_2d(&tmB, g.w, (uint64_t)N, (uint64_t)planes_in * K, (uint64_t)ldw, 128, BK))) return rc;  // half W tiles
     p.num_m_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
@@ -743,6 +780,7 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
         return f16 ? pair::launch_pair<ZK_EPI_BIAS_GELU_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream)
                    : pair::launch_pair<ZK_EPI_BIAS_GELU_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
       case ZK_EPI_BIAS_RESID_F32:
+        if (seg) return pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16, true>(tmA, tmB, tmC, p, cls(cls_resid), stream);
         return f16 ? pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16>(tmA, tmB, tmC, p, cls(cls_resid), stream)
                    : pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(cls_resid), stream);
       case ZK_EPI_BIAS_SPLIT: return pair::launch_pair<ZK_EPI_BIAS_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);
@@ -758,6 +796,7 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
       return f16 ? launch<ZK_EPI_BIAS_GELU_BF16, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream)
                  : launch<ZK_EPI_BIAS_GELU_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
     case ZK_EPI_BIAS_RESID_F32:
+      if (seg) return launch<ZK_EPI_BIAS_RESID_F32, FMT_F16, true>(tmA, tmB, tmC, p, cls(cls_resid), stream);
       return f16 ? launch<ZK_EPI_BIAS_RESID_F32, FMT_F16>(tmA, tmB, tmC, p, cls(cls_resid), stream)
                  : launch<ZK_EPI_BIAS_RESID_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(cls_resid), stream);
     case ZK_EPI_PATCH_F32:

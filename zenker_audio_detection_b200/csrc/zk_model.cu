@@ -376,6 +376,7 @@ void zk_model_destroy(zk_model* m) {
 }
 
 int zk_model_num_tokens(const zk_model* m) { return m ? m->tokens : 0; }
+int zk_model_max_length(const zk_model* m) { return m ? m->max_length : 0; }
 
 size_t zk_model_workspace_bytes(const zk_model* m, int batch, int precision) {
   if (!m || batch <= 0) return 0;

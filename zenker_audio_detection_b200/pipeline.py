@@ -17,6 +17,7 @@ differ in more than mean/std, the per-window contract kernels are used instead (
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Union
 
@@ -88,6 +89,7 @@ class TwoStagePipeline:
                       and fx_s1.num_mel_bins == 128 and self.m1.max_length == fx_s1.max_length == self.m2.max_length)
         self.valid_frames = min(ops.FbankPlan.num_frames(self.win), fx_s1.max_length)
         self.plan = fx_s1._get_plan(self.device)
+        self._ws: Optional[torch.Tensor] = None  # zk_cascade_run workspace (fbank, logits, model activations)
 
     # ------------------------------------------------------------------ stages
     def _stage_logits(self, model: ZenkerASTForAudioClassification, fx: ZenkerASTFeatureExtractor, audio: torch.Tensor,
@@ -135,29 +137,70 @@ class TwoStagePipeline:
             _, _, n = cascade.window_geometry(L, self.window_sec, self.hop_sec)
             if L < self.win:  # ref:70-73: only a too-short recording is zero padded
                 audio = torch.cat([audio, torch.zeros(self.win - L, dtype=torch.float32, device=audio.device)])
-            fbank = self.plan.fbank(audio) if self.fused else None
-            logits1 = self._stage_logits(self.m1, self.fx1, audio, fbank, n, None)
-            if logits1.dim() != 2 or logits1.shape[1] != 2:
-                raise RuntimeError("Stage1 output shape unexpected; expected (N,2)")  # ref:310-311
-            re1 = self._recheck(self.m1, self.fx1, audio, fbank, logits1, None, self.margins1)
-            probs1, pred, index, count = ops.gate_compact(logits1, self.thr1, self.min_prob)
-            k = int(count.item())  # Stage 2's batch count depends on it
-            re2 = 0
-            if k:
-                logits2 = self._stage_logits(self.m2, self.fx2, audio, fbank, k, index)
-                if logits2.shape[1] != 2:
-                    raise RuntimeError("Stage2 output shape unexpected; expected (K,2)")  # ref:325-326
-                re2 = self._recheck(self.m2, self.fx2, audio, fbank, logits2, index, self.margins2)
-                probs2 = ops.softmax2(logits2)
+            if self.fused and self.m1.num_labels == 2 and self.m2.num_labels == 2:
+                s1, s1_preds, idx, s2, re1, re2 = self._run_fused(audio.contiguous(), n)
             else:
-                probs2 = torch.zeros((0, 2), dtype=torch.float32, device=self.device)
-            s1 = probs1.cpu().numpy()
-            s1_preds = pred.cpu().numpy().astype(np.int64)
-            idx = index[:k].cpu().numpy().astype(np.int64)
-            s2 = probs2.cpu().numpy()
+                s1, s1_preds, idx, s2, re1, re2 = self._run_stepwise(audio, n)
         classes = cascade.stage2_classes(n, idx, s2, self.thr2, self.stage2_argmax)
         summary = cascade.summarize_stage_outputs(s1, idx, s2, self.thr2, self.stage2_argmax)
         return RecordingResult(n, s1, s1_preds, idx, s2, classes, summary, re1, re2)
+
+    def _run_fused(self, audio: torch.Tensor, n: int):
+        """One ``zk_cascade_run`` call (include/zk_b200.h section 6): fbank, both stages, re-checks, gate."""
+        lib = _lib.load()
+        p = _lib.CascadeParams(
+            batch_size=self.batch_size, recheck_batch=self.recheck_batch, window_samples=self.win, hop_samples=self.hop,
+            mean1=float(self.fx1.mean), std1=float(self.fx1.std), mean2=float(self.fx2.mean), std2=float(self.fx2.std),
+            thr1=self.thr1, min_prob=-1.0 if self.min_prob is None else float(self.min_prob), thr2=self.thr2,
+            stage2_argmax=1 if self.stage2_argmax else 0, recheck_eps=float(self.recheck_eps))
+        h1, h2 = self.m1.engine._h, self.m2.engine._h
+        need = int(lib.zk_cascade_workspace_bytes(h1, h2, audio.numel(), C.byref(p)))
+        if need == 0:
+            raise ZkError(f"zk_cascade_workspace_bytes: {_lib.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        probs1 = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        pred = torch.empty((n,), dtype=torch.int32, device=self.device)
+        index = torch.empty((n,), dtype=torch.int32, device=self.device)
+        probs2 = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        counts = _lib.CascadeCounts()
+        _lib.check(lib.zk_cascade_run(self.plan._h, h1, h2, audio.data_ptr(), audio.numel(), C.byref(p), self._ws.data_ptr(),
+                                      self._ws.numel(), probs1.data_ptr(), pred.data_ptr(), index.data_ptr(),
+                                      probs2.data_ptr(), C.byref(counts), _lib.stream_ptr()), "zk_cascade_run")
+        if counts.num_windows != n:
+            raise RuntimeError(f"window count mismatch: {counts.num_windows} != {n}")
+        k = int(counts.num_forwarded)
+        s1 = probs1.cpu().numpy()  # the D2H copies below wait for the stream
+        s1_preds = pred.cpu().numpy().astype(np.int64)
+        idx = index[:k].cpu().numpy().astype(np.int64)
+        s2 = probs2[:k].cpu().numpy() if k else np.zeros((0, 2), dtype=np.float32)
+        return s1, s1_preds, idx, s2, int(counts.rechecked_s1), int(counts.rechecked_s2)
+
+    def _run_stepwise(self, audio: torch.Tensor, n: int):
+        """The same cascade driven step by step from Python: the route for window / hop geometries the fused gather does
+        not cover (per-window contract kernels), and the cross-check of ``zk_cascade_run`` in the tests."""
+        fbank = self.plan.fbank(audio) if self.fused else None
+        logits1 = self._stage_logits(self.m1, self.fx1, audio, fbank, n, None)
+        if logits1.dim() != 2 or logits1.shape[1] != 2:
+            raise RuntimeError("Stage1 output shape unexpected; expected (N,2)")  # ref:310-311
+        re1 = self._recheck(self.m1, self.fx1, audio, fbank, logits1, None, self.margins1)
+        probs1, pred, index, count = ops.gate_compact(logits1, self.thr1, self.min_prob)
+        k = int(count.item())  # Stage 2's batch count depends on it
+        re2 = 0
+        if k:
+            logits2 = self._stage_logits(self.m2, self.fx2, audio, fbank, k, index)
+            if logits2.shape[1] != 2:
+                raise RuntimeError("Stage2 output shape unexpected; expected (K,2)")  # ref:325-326
+            re2 = self._recheck(self.m2, self.fx2, audio, fbank, logits2, index, self.margins2)
+            probs2 = ops.softmax2(logits2)
+        else:
+            probs2 = torch.zeros((0, 2), dtype=torch.float32, device=self.device)
+        s1 = probs1.cpu().numpy()
+        s1_preds = pred.cpu().numpy().astype(np.int64)
+        idx = index[:k].cpu().numpy().astype(np.int64)
+        s2 = probs2.cpu().numpy()
+        return s1, s1_preds, idx, s2, re1, re2
 
     def resample_to_device(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> torch.Tensor:
         """ref:53-59 (``load_audio`` after the decode): H2D, channel mean, resample -> CUDA float32 mono 16 kHz."""
