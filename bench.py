@@ -23,6 +23,12 @@ windows/s counts Stage-1 windows; the Stage-2 work is inside the time but not in
 
 N > 1 (torchrun): every rank runs its own recording per step (weak scaling, recordings are independent) and the
 per-window score records are all-gathered over NCCL inside the timed region, as the path does after its last stage.
+
+--workload cfg4 (BASELINE.json configs[3], run_batch_simple_2stage.py:273-291 + ref:361-382): a FIXED pool of recordings
+of unequal length (two per patient) is dealt to the ranks longest-first (dist.shard_recordings), every rank runs its
+shard from pinned host memory, ONE gather of the 24-byte window records ends the step and rank 0 builds the per-patient
+documents.  Strong scaling: the pool does not grow with N.  Reports per-rank busy time, imbalance and the gather's
+share, and checks (outside the timing) that a recording processed on another rank gives bit-identical records.
 """
 from __future__ import annotations
 
@@ -550,6 +556,16 @@ def run_ours(args):
     }
     if rank == 0:
         line["secondary"] = secondary_metrics(device, peaks, pipe.m2.engine)
+        # the same steps with the decision re-check switched off (recheck_eps = 0): what the re-check costs on THESE
+        # weights, whose margins are two orders of magnitude narrower than a trained classifier's
+        if world == 1:  # (single process only: step() takes part in the collective under torchrun)
+            eps = pipe.recheck_eps
+            pipe.recheck_eps = 0.0
+            step(wave_dev)
+            ms_off, n_off, _, _, _ = timed(wave_dev, args.steps, False)
+            pipe.recheck_eps = eps
+            line["secondary"]["recheck_off"] = {"windows_per_s": n_off / (ms_off / 1000.0), "ms_per_step": ms_off / args.steps,
+                                                "note": "decisions NOT guaranteed equal to the fp32 reference's in this mode"}
         if not args.skip_library:
             dt = torch.float16 if operand_format == "fp16" else torch.bfloat16
             try:
@@ -573,6 +589,133 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_cfg4(args):
+    """Strong-scaling patient batch (see the module docstring)."""
+    import torch.distributed as dist
+
+    from zenker_audio_detection_b200 import _lib, dist as zdist, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the zenker-b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.require_device()
+
+    R = int(args.pool)
+    lo, hi = (float(v) for v in args.pool_seconds.split(","))
+    rng = np.random.default_rng(4004)
+    seconds = [float(v) for v in rng.uniform(lo, hi, size=R)]
+    lengths = [int(round(sec * 48000)) for sec in seconds]
+    patients = [[2 * i, 2 * i + 1] for i in range(R // 2)]
+    shards = zdist.shard_recordings(lengths, world)
+    mine = shards[rank]
+    pipe, sd1 = build_pipeline(args, device)
+    calib = torch.from_numpy(synth.recording(120.0, 48000, seed=4000)).to(device)  # the same on every rank
+    calibrate_gate(pipe, sd1, calib, args.stage2_fraction, device)
+    del calib
+    hosts = {i: torch.from_numpy(synth.recording(seconds[i], 48000, seed=4100 + i)).pin_memory() for i in mine}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step():
+        t0 = time.perf_counter()
+        blocks, n, k, re = [], 0, 0, 0
+        for i in mine:
+            r = pipe.run_waveform(hosts[i], 48000)
+            blocks.append(zdist.pack_records(i, r.s1_probs, r.swallow_indices, r.s2_probs))
+            n += r.num_windows
+            k += len(r.swallow_indices)
+            re += r.rechecked_s1 + r.rechecked_s2
+        torch.cuda.synchronize()
+        busy = time.perf_counter() - t0
+        local_rec = np.concatenate(blocks) if blocks else np.zeros((0, zdist.RECORD_WIDTH), dtype=np.int32)
+        allrec = zdist.all_gather_records(local_rec, device)
+        docs = None
+        if rank == 0:
+            docs = zdist.patient_documents(zdist.unpack_records(allrec), patients, pipe.thr2, pipe.stage2_argmax)
+        return busy, time.perf_counter() - t0, n, k, re, allrec, docs
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        if mine:
+            pipe.run_waveform(hosts[mine[0]], 48000)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    busy_s, wall_s, n_tot, k_tot, re_tot = 0.0, 0.0, 0, 0, 0
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            b, w, n, k, re, allrec, docs = one_step()
+            busy_s += b
+            wall_s += w
+            n_tot += n
+            k_tot += k
+            re_tot += re
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    stats = torch.tensor([ms, busy_s * 1e3, n_tot, k_tot, re_tot], dtype=torch.float64, device=device)
+    allstats = torch.zeros((world, 5), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_gather_into_tensor(allstats.view(-1), stats)
+    else:
+        allstats[0] = stats
+    allstats = allstats.cpu().numpy()
+    # bit-identity across ranks: re-run the first recording of the NEXT rank's shard here and compare with what it sent
+    ok = 1
+    other = shards[(rank + 1) % world]
+    if world > 1 and other:
+        i = other[0]
+        r = pipe.run_waveform(torch.from_numpy(synth.recording(seconds[i], 48000, seed=4100 + i)).pin_memory(), 48000)
+        mine_rec = zdist.pack_records(i, r.s1_probs, r.swallow_indices, r.s2_probs)
+        theirs = allrec[allrec[:, 0] == i]
+        ok = int(theirs.shape == mine_rec.shape and np.array_equal(theirs[np.argsort(theirs[:, 1])], mine_rec))
+    okt = torch.tensor([ok], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        step_ms = float(allstats[:, 0].max())
+        busy = allstats[:, 1] / args.steps
+        n_all = int(allstats[:, 2].sum())
+        line = {
+            "metric": METRIC, "value": n_all / (step_ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": pipe.m1.operand_format, "data": "synthetic",
+            "config": {"workload": f"cfg4: patient-level batch, a fixed pool of {R} synthetic 48 kHz recordings of U({lo:.0f},{hi:.0f}) s "
+                                   f"({R // 2} patients x 2 files) sharded longest-first over {world} GPU(s), one gather per step",
+                       "batch_size": args.batch_size, "windows_per_step": n_all // args.steps,
+                       "stage2_fraction": round(float(allstats[:, 3].sum()) / max(1, n_all), 4),
+                       "l2": "activation working set >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": n_all / (step_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(sum(lengths) * 4),
+                    "d2h_bytes_per_step": int(n_all // args.steps * 12 + float(allstats[:, 3].sum()) / args.steps * 12),
+                    "note": "this workload is timed end to end only: every recording starts in pinned host memory"},
+            "gpu_launches": None,
+            "clocks": clk.summary(),
+            "sharding": {"recordings_per_rank": [len(s) for s in shards],
+                         "audio_seconds_per_rank": [round(sum(seconds[i] for i in s), 1) for s in shards],
+                         "busy_ms_per_rank_per_step": [round(float(v), 2) for v in busy],
+                         "imbalance_max_over_mean": float(busy.max() / busy.mean()),
+                         "gather_and_join_ms_per_step": round(step_ms / args.steps - float(busy.max()), 2),
+                         "what_sets_the_gap": "the slowest rank's busy time (longest-first sharding leaves at most one recording "
+                                              "of imbalance; the GPUs also run at different power-capped clocks); the gather is "
+                                              "24 B per window"},
+            "rechecked_windows_per_step": float(allstats[:, 4].sum()) / args.steps,
+            "records_bit_identical_across_ranks": bool(int(okt.item()) == 1) if world > 1 else None,
+            "patients": len(docs) if docs is not None else None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -584,9 +727,14 @@ def main():
     ap.add_argument("--stage2-fraction", type=float, default=0.3)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--skip-library", action="store_true", help="skip the library-kernel / HF-on-B200 comparisons")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--pool", type=int, default=64, help="cfg4: recordings in the fixed pool (2 per patient)")
+    ap.add_argument("--pool-seconds", default="90,150", help="cfg4: recording lengths are U(lo,hi) seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     else:
         run_ours(args)
 

@@ -92,6 +92,15 @@ int zk_fx_contract_f32(const zk_fbank_plan* plan, const float* d_windows, int ba
                        int64_t win_pitch, int do_normalize, float mean, float std, int max_length, float* d_out,
                        zk_stream_t stream);
 
+/* Dataset normalisation statistics as an EPILOGUE of the feature kernel (utils/compute_ast_normalization_stats.py:
+ * 62-80: extractor with do_normalize = False, float64 sum and sum of squares over every element of the zero-padded
+ * (B, max_length, 128) features): the un-normalised log-mel values of `batch` waveforms are added to d_acc[0] (sum) and
+ * d_acc[1] (sum of squares) in fp64 while they are computed; d_out [batch][max_length][128] receives the features, or
+ * is NULL for statistics only (nothing but 16 bytes leaves the SMs).  The caller zeroes d_acc and counts
+ * batch * max_length * 128 elements per call. */
+int zk_fx_stats_f32(const zk_fbank_plan* plan, const float* d_windows, int batch, int64_t win_len, int64_t win_pitch,
+                    int max_length, float* d_out, double* d_acc, zk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (4) AST forward -- replaces ASTForAudioClassification.forward (HF:modeling_audio_spectrogram_
  *     transformer.py:403-451) for the AST-base geometry (hidden 768, 12 layers, 12 heads, MLP 3072,

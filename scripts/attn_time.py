@@ -13,7 +13,7 @@ B, T = int(os.environ.get("ZK_BENCH_BATCH", "128")), 1214
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B * T, 2304, device="cuda", generator=g)
 qkv[:, :1536] *= 2.0
-qkv = qkv.to(torch.bfloat16)
+qkv = qkv.to(torch.bfloat16 if os.environ.get("ZK_OPERANDS", "fp16").lower().startswith("b") else torch.float16)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(5):
     ops.attention(qkv, B, T)

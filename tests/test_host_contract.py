@@ -124,7 +124,10 @@ def _gloo_worker(rank, world, port, q):
     local = np.concatenate(blocks) if blocks else np.zeros((0, zdist.RECORD_WIDTH))
     allrec = zdist.all_gather_records(local, torch.device("cpu"))
     per = zdist.unpack_records(allrec)
+    assert allrec.dtype == np.int32 and allrec.shape[1] == 6  # 24 bytes per window on the wire
     summ = {rid: cascade.summarize_stage_outputs(*per[rid], 0.5) for rid in sorted(per)}
+    docs = zdist.patient_documents(per, [[0, 1], [2, 3]], 0.5)  # ref:361-382: two files per patient
+    assert docs[0]["aggregate"] == cascade.aggregate_patient(docs[0]["per_file"], ["rec0", "rec1"])
     q.put((rank, json.dumps(summ, sort_keys=True)))
     dist.destroy_process_group()
 
@@ -154,3 +157,59 @@ def test_all_gather_records_gloo(world):
         s2 = g.random((len(idx), 2)).astype(np.float32)
         ref[rid] = cascade.summarize_stage_outputs(s1, idx, s2, 0.5)
     assert json.loads(outs[0]) == json.loads(json.dumps({str(k): v for k, v in ref.items()}, sort_keys=True))
+
+
+def _plan_worker(rank, world, port, root, q):
+    """batch.plan_patients under two ranks where rank 1 arrives late and rank 0 has ALREADY written a result file: the
+    plan is rank 0's, broadcast, so both ranks shard the same list (per-rank os.path.exists plans diverge)."""
+    import time
+
+    from zenker_audio_detection_b200 import batch
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    args = batch.build_arg_parser().parse_args(["--fold", "1", "--ids-root", os.path.join(root, "ids"), "--long-audio-root",
+                                                os.path.join(root, "long"), "--output-dir", os.path.join(root, "out")])
+    if rank == 0:
+        todo, _ = batch.global_plan(args)  # what the plan looks like before anything was written
+        q.put(("before", sorted(p for p, _, _ in todo)))
+    else:
+        time.sleep(1.0)  # a slow starter: by now rank 0's first result exists on disk
+    if rank == 0:
+        with open(os.path.join(root, "out", "11_2stage.json"), "w") as f:
+            f.write("{}")
+    mine, _ = batch.plan_patients(args, rank, world)
+    q.put((rank, sorted(p for p, _ in mine)))
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+
+
+def test_batch_plan_is_made_once_and_broadcast(tmp_path):
+    import torch.multiprocessing as mp
+
+    from zenker_audio_detection_b200 import wavio
+
+    root = tmp_path
+    (root / "ids").mkdir()
+    (root / "out").mkdir()
+    pids = ["11", "22", "33", "44"]
+    (root / "ids" / "test_ids_fold1.txt").write_text("".join(f"Healthy/{p}\n" for p in pids))
+    for i, pid in enumerate(pids):
+        d = root / "long" / "Healthy" / pid
+        d.mkdir(parents=True)
+        for k in range(2):
+            wavio.write_pcm16(str(d / f"r{k}.wav"), np.zeros((1, 400 * (i + 1)), dtype=np.float32), 16000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, str(root), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # rank 0 planned AFTER writing 11's result in this test, so 11 is skipped for everyone -- the point is that both
+    # ranks hold the SAME plan: disjoint shards whose union is exactly rank 0's todo list
+    assert got["before"] == sorted(pids)
+    assert sorted(got[0] + got[1]) == ["22", "33", "44"] and not set(got[0]) & set(got[1])

@@ -75,6 +75,8 @@ SIGNATURES = {
     "zk_fbank_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "zk_fx_contract_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                      C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "zk_fx_stats_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
     "zk_model_create": (C.c_int, [C.POINTER(AstWeights), C.POINTER(C.c_void_p)]),
     "zk_model_destroy": (None, [C.c_void_p]),
     "zk_model_num_tokens": (C.c_int, [C.c_void_p]),

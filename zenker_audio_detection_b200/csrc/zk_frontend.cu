@@ -65,6 +65,8 @@ struct Job {
   long long num_tiles;
   int normalize;
   float mean, std2;
+  double* stats;         // optional: stats[0] += sum(v), stats[1] += sum(v^2) over every value computed (fp64)
+  int store;             // 0: statistics only, nothing is written to `out`
 };
 
 // Scalar shared-memory load that the compiler cannot fuse with its neighbours: nvcc 12.9 turns the loads of
@@ -138,9 +140,11 @@ __global__ void __launch_bounds__(THREADS, 1) fbank_kernel(const zk_fbank_plan p
     bulk_load_1d(samples, src, bytes, &bar[0]);
   }
 
+  double st_sum = 0.0, st_sq = 0.0;  // this thread's share of the dataset statistics (job.stats)
   int it = 0;
   for (long long tile = blockIdx.x; tile < job.num_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
+    float ts = 0.f, tq = 0.f;  // fp32 within a tile (a thread adds at most a few hundred values), fp64 across tiles
     const float* src;
     int nf;
     long long out_row;
@@ -242,11 +246,34 @@ __global__ void __launch_bounds__(THREADS, 1) fbank_kernel(const zk_fbank_plan p
           va = __fdiv_rn(__fsub_rn(va, job.mean), job.std2);
           vb = __fdiv_rn(__fsub_rn(vb, job.mean), job.std2);
         }
-        if (live_a) dst_a[16 * i] = va;
-        if (live_b) dst_b[16 * i] = vb;
+        if (live_a && job.store) dst_a[16 * i] = va;
+        if (live_b && job.store) dst_b[16 * i] = vb;
+        if (job.stats) {
+          if (live_a) {
+            ts += va;
+            tq = fmaf(va, va, tq);
+          }
+          if (live_b) {
+            ts += vb;
+            tq = fmaf(vb, vb, tq);
+          }
+        }
       }
     }
+    st_sum += (double)ts;
+    st_sq += (double)tq;
     __syncthreads();  // every warp is done with xs_tile (and its scratch) before the tile buffer is refilled
+  }
+  if (job.stats) {  // utils/compute_ast_normalization_stats.py:77-80 as an epilogue: one fp64 atomic pair per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
+      st_sq += __shfl_xor_sync(0xffffffffu, st_sq, o);
+    }
+    if (lane == 0) {
+      atomicAdd(job.stats, st_sum);
+      atomicAdd(job.stats + 1, st_sq);
+    }
   }
 }
 
@@ -723,6 +750,8 @@ int zk_fbank_f32(const zk_fbank_plan* plan, const float* d_wave, int64_t n, floa
   job.normalize = 0;
   job.mean = 0.f;
   job.std2 = 1.f;
+  job.stats = nullptr;
+  job.store = 1;
   return launch_fbank(plan, job, (cudaStream_t)stream);
 }
 
@@ -768,6 +797,53 @@ int zk_fx_contract_f32(const zk_fbank_plan* plan, const float* d_windows, int ba
   job.normalize = do_normalize;
   job.mean = mean;
   job.std2 = std2;
+  job.stats = nullptr;
+  job.store = 1;
+  return launch_fbank(plan, job, (cudaStream_t)stream);
+}
+
+int zk_fx_stats_f32(const zk_fbank_plan* plan, const float* d_windows, int batch, int64_t win_len, int64_t win_pitch,
+                    int max_length, float* d_out, double* d_acc, zk_stream_t stream) {
+  using namespace zk::fbk;
+  int rc = zk::device_check();
+  if (rc) return rc;
+  if (!plan || batch < 0 || win_len < 0 || win_pitch < win_len || max_length <= 0 || !d_acc || (batch > 0 && !d_windows)) {
+    zk::set_error("zk_fx_stats_f32: bad arguments");
+    return ZK_ERR_ARG;
+  }
+  {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != plan->device) {
+      zk::set_error("zk_fx_stats_f32: the plan belongs to device %d but the current device is %d", plan->device, cur);
+      return ZK_ERR_ARG;
+    }
+  }
+  if (batch == 0) return 0;
+  const int64_t m = zk_fbank_num_frames(win_len);
+  const int rows = (int)(m < max_length ? m : max_length);
+  if (d_out && rows < max_length) {  // zero padding (do_normalize = False): adds nothing to the sums
+    long long total = (long long)batch * (max_length - rows) * (NMEL / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8LL * zk::num_sms()) blocks = 8LL * zk::num_sms();
+    zk::ProfScope prof(ZK_K_MISC, (cudaStream_t)stream);
+    fill_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, batch, rows, max_length, 0.0f);
+    ZK_LAUNCH_CHECK("fill_pad_kernel");
+  }
+  if (rows == 0) return 0;
+  Job job;
+  job.wave = d_windows;
+  job.out = d_out;
+  job.src_pitch = win_pitch;
+  job.out_pitch = max_length;
+  job.seg_frames = rows;
+  job.tiles_per_seg = (rows + TILE_FRAMES - 1) / TILE_FRAMES;
+  job.num_tiles = (long long)job.tiles_per_seg * batch;
+  job.normalize = 0;
+  job.mean = 0.f;
+  job.std2 = 1.f;
+  job.stats = d_acc;
+  job.store = d_out ? 1 : 0;
   return launch_fbank(plan, job, (cudaStream_t)stream);
 }
 

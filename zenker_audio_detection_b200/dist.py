@@ -3,8 +3,9 @@ no data-path collective; the only communication is the fi
 records, one ``all_gather`` of counts followed by one ``all_gather`` of a padded record buffer (NCCL has no
 allgatherv).  The same code runs on ``gloo`` for the CPU tests.
 
-Record layout (float64 x 7 per window, exact for int32 ids and float32 probabilities):
-    [recording_id, window_index, p_s1_0, p_s1_1, forwarded (0/1), p_s2_0, p_s2_1]  (p_s2 = NaN if not forwarded)
+Record layout (24 bytes per window): six 32-bit words
+    [recording_id i32, window_index i32, p_s1_0 f32, p_s1_1 f32, p_s2_0 f32, p_s2_1 f32]   (p_s2 = NaN if not forwarded)
+carried as an int32 matrix (the float words bit-cast), so ids and probabilities both travel exactly.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 import torch
 
-RECORD_WIDTH = 7
+RECORD_WIDTH = 6  # 32-bit words
 
 
 def shard_recordings(lengths: Sequence[int], world_size: int) -> List[List[int]]:
@@ -32,15 +33,16 @@ def shard_recordings(lengths: Sequence[int], world_size: int) -> List[List[int]]
 
 
 def pack_records(recording_id: int, s1_probs: np.ndarray, swallow_indices: np.ndarray, s2_probs: np.ndarray) -> np.ndarray:
+    """-> (n, 6) int32 record block of one recording (see the module docstring)."""
     n = len(s1_probs)
-    rec = np.full((n, RECORD_WIDTH), np.nan, dtype=np.float64)
-    rec[:, 0] = recording_id
-    rec[:, 1] = np.arange(n)
-    rec[:, 2:4] = s1_probs
-    rec[:, 4] = 0.0
+    f = np.full((n, 4), np.nan, dtype=np.float32)
+    f[:, 0:2] = s1_probs
     if len(swallow_indices):
-        rec[swallow_indices, 4] = 1.0
-        rec[swallow_indices, 5:7] = s2_probs
+        f[swallow_indices, 2:4] = s2_probs
+    rec = np.empty((n, RECORD_WIDTH), dtype=np.int32)
+    rec[:, 0] = recording_id
+    rec[:, 1] = np.arange(n, dtype=np.int32)
+    rec[:, 2:6] = f.view(np.int32)
     return rec
 
 
@@ -49,30 +51,50 @@ def unpack_records(rec: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, n
     out: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]] = {}
     if len(rec) == 0:
         return out
+    rec = np.ascontiguousarray(rec, dtype=np.int32)
     ids = rec[:, 0].astype(np.int64)
     for rid in np.unique(ids):
         r = rec[ids == rid]
-        r = r[np.argsort(r[:, 1], kind="stable")]
-        fwd = np.where(r[:, 4] == 1.0)[0].astype(np.int64)
-        out[int(rid)] = (r[:, 2:4].astype(np.float32), fwd, r[fwd, 5:7].astype(np.float32))
+        r = np.ascontiguousarray(r[np.argsort(r[:, 1], kind="stable")])
+        f = r[:, 2:6].copy().view(np.float32)
+        fwd = np.where(~np.isnan(f[:, 2]))[0].astype(np.int64)
+        out[int(rid)] = (f[:, 0:2].copy(), fwd, f[fwd, 2:4].copy())
     return out
 
 
 def all_gather_records(local: np.ndarray, device: torch.device) -> np.ndarray:
-    """Gather every rank's (n_r, 7) record block to every rank; returns them concatenated in rank order."""
+    """Gather every rank's (n_r, 6) int32 record block to every rank; returns them concatenated in rank order.
+    Two collectives: the counts, then one padded buffer (NCCL has no allgatherv); 24 bytes per window on the wire."""
     import torch.distributed as dist
 
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
     count = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(count) for _ in range(world)]
-    dist.all_gather(counts, count)
-    counts_h = [int(c.item()) for c in counts]
+    counts = torch.zeros((world,), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, count)
+    counts_h = [int(c) for c in counts.cpu()]
     cap = max(max(counts_h), 1)
-    buf = torch.zeros((cap, RECORD_WIDTH), dtype=torch.float64, device=device)
+    buf = torch.zeros((cap, RECORD_WIDTH), dtype=torch.int32, device=device)
     if local.shape[0]:
-        buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
-    gathered = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(gathered, buf)
-    return np.concatenate([g[:c].cpu().numpy() for g, c in zip(gathered, counts_h)], axis=0)
+        buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.int32)).to(device)
+    gathered = torch.empty((world * cap, RECORD_WIDTH), dtype=torch.int32, device=device)  # rank blocks along dim 0
+    dist.all_gather_into_tensor(gathered, buf)
+    g = gathered.view(world, cap, RECORD_WIDTH).cpu().numpy()
+    return np.concatenate([g[r, :c] for r, c in enumerate(counts_h)], axis=0)
+
+
+def patient_documents(records: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]], patients: Sequence[Sequence[int]],
+                      stage2_threshold: float, stage2_argmax: bool = False) -> List[Dict]:
+    """ref:361-382 after the gather: per-file summaries (ref:148-195) and the aggregate of each patient's recordings."""
+    from . import cascade
+
+    docs = []
+    for files in patients:
+        names = [f"rec{int(i)}" for i in files]
+        per_file = {}
+        for name, i in zip(names, files):
+            s1, idx, s2 = records[int(i)]
+            per_file[name] = cascade.summarize_stage_outputs(s1, idx, s2, stage2_threshold, stage2_argmax)
+        docs.append({"per_file": per_file, "aggregate": cascade.aggregate_patient(per_file, names)})
+    return docs

@@ -224,6 +224,22 @@ class FeatureStats:
         self.acc = torch.zeros(2, dtype=torch.float64, device=device or torch.device("cuda", torch.cuda.current_device()))
         self.count = 0
 
+    def update_from_waveforms(self, plan: "FbankPlan", windows: torch.Tensor, max_length: int,
+                              return_features: bool = False) -> Optional[torch.Tensor]:
+        """``windows``: CUDA float32 ``(B, samples)`` equal-length waveforms.  Their un-normalised features are summed
+        INSIDE the feature kernel (``zk_fx_stats_f32``); nothing is written unless ``return_features``."""
+        lib = _lib.load()
+        w = _cuda(windows, torch.float32, "FeatureStats.update_from_waveforms")
+        if w.dim() != 2:
+            raise ZkError("update_from_waveforms: expected (batch, samples)")
+        b, n = w.shape
+        out = torch.empty((b, max_length, 128), dtype=torch.float32, device=w.device) if return_features else None
+        if b:
+            check(lib.zk_fx_stats_f32(plan._h, w.data_ptr(), b, n, n, max_length, out.data_ptr() if out is not None else None,
+                                      self.acc.data_ptr(), _lib.stream_ptr()), "zk_fx_stats_f32")
+        self.count += b * max_length * 128
+        return out
+
     def update(self, feats: torch.Tensor, padded_elements: Optional[int] = None) -> None:
         """``feats``: CUDA float32, any shape.  ``padded_elements``: element count of the padded tensor these values
         stand for (zero padding adds nothing to the sums; e.g. a compact (98,128) window counts as 1024*128)."""
