@@ -303,6 +303,48 @@ def gold_cascade_cfg2():
                         n_windows=len(windows), audio16k_head=audio[:64], **out)
 
 
+def gold_stats():
+    """utils/compute_ast_normalization_stats.py: its module imports librosa / soundfile (absent here), so the two pure
+    functions are taken out of the reference source with ``ast`` and executed as they are: ``aggregate_stats`` on a
+    5-fold example, and the mean / unbiased-std tail of ``compute_fold_stats`` (lines 82-95) through a features-only
+    re-run of its accumulation loop on HF extractor output (do_normalize = False, lines 62-80)."""
+    import ast
+
+    src = open("/root/reference/utils/compute_ast_normalization_stats.py").read()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch, "os": os}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "aggregate_stats":
+            exec(compile(ast.Module([node], []), "ref_stats", "exec"), ns)
+    rng = np.random.default_rng(5)
+    per_fold = [{"fold": k + 1, "mean": float(rng.normal(-4.0, 0.3)), "std": float(rng.uniform(4.0, 5.0)),
+                 "count": int(rng.integers(1, 50)) * 131072} for k in range(5)]
+    per_fold.append({"fold": 6, "mean": 0.0, "std": 0.0, "count": 0})
+    agg = ns["aggregate_stats"](per_fold)
+    # the accumulation of lines 62-95 on 6 snippets of three lengths (one shorter than a window, one over 10.24 s)
+    from transformers import ASTFeatureExtractor
+
+    fx = ASTFeatureExtractor(max_length=1024, num_mel_bins=128)
+    fx.do_normalize = False
+    g = torch.Generator().manual_seed(9)
+    wavs = [(torch.randn(n, generator=g) * a).numpy() for n, a in ((16000, 0.1), (16000, 0.01), (8000, 0.3), (8000, 0.05),
+                                                                   (170000, 0.2), (170000, 0.02))]
+    total_count, running_sum, running_sq_sum = 0, 0.0, 0.0
+    for start in range(0, len(wavs), 4):
+        feats = fx(wavs[start:start + 4], sampling_rate=16000, return_tensors="pt")["input_values"]
+        flat = feats.view(feats.size(0), -1).to(torch.float64)
+        running_sum += flat.sum().item()
+        running_sq_sum += (flat ** 2).sum().item()
+        total_count += flat.numel()
+    mean = running_sum / total_count
+    var = max(running_sq_sum / total_count - mean * mean, 0.0) * (total_count / (total_count - 1))
+    with open(os.path.join(GOLD, "stats_golden.json"), "w") as f:
+        json.dump({"per_fold": per_fold, "aggregate": agg, "snippet_lengths": [len(w) for w in wavs],
+                   "snippet_gains": [0.1, 0.01, 0.3, 0.05, 0.2, 0.02], "snippet_seed": 9,
+                   "fold_stats": {"mean": mean, "std": var ** 0.5, "count": total_count}}, f, indent=1)
+    print("stats", agg, mean, var ** 0.5, total_count)
+
+
 CACHE_FIXTURE_DIR = "/tmp/zk_cache_golden"  # absolute on purpose: the cache key hashes the absolute path (refc:97-100)
 
 
@@ -373,7 +415,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "cache", "ast", "astplain", "cascade60"]
+    todo = a.only.split(",") if a.only else ["windows", "cascade", "fx", "resample", "cache", "stats", "ast", "astplain", "cascade60"]
     if "windows" in todo:
         gold_windows()
     if "cascade" in todo:
@@ -384,6 +426,8 @@ if __name__ == "__main__":
         gold_resample()
     if "cache" in todo:
         gold_cache()
+    if "stats" in todo:
+        gold_stats()
     if not a.skip_ast:
         if "ast" in todo:
             gold_ast()

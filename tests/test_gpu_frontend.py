@@ -153,3 +153,54 @@ def test_resample_pcm16():
     ref = thirdparty.resample((pcm.astype(np.float32) / 32768.0).T.copy(), 48000, 16000)
     got = ops.resample(torch.from_numpy(pcm).cuda(), 48000, 16000).cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-6
+
+
+def test_stats_epilogue_and_cli_match_the_reference_accumulation(golden_dir, tmp_path):
+    """zk_fx_stats_f32 (sums inside the feature kernel, nothing written) and `python -m ...stats` on WAV files against the
+    reference's accumulation loop run on the HF extractor (golden: utils/compute_ast_normalization_stats.py:62-95)."""
+    import json
+    import os
+
+    from zenker_audio_detection_b200 import ops, stats, wavio
+
+    g = json.load(open(os.path.join(golden_dir, "stats_golden.json")))
+    gen = torch.Generator().manual_seed(int(g["snippet_seed"]))
+    wavs = [(torch.randn(n, generator=gen) * a) for n, a in zip(g["snippet_lengths"], g["snippet_gains"])]
+    ref = g["fold_stats"]
+    plan = ops.FbankPlan()
+    st = ops.FeatureStats()
+    feats = None
+    for n in sorted(set(g["snippet_lengths"])):
+        group = torch.stack([w for w in wavs if w.numel() == n]).cuda()
+        out = st.update_from_waveforms(plan, group, 1024, return_features=(n == 16000))
+        if out is not None:
+            feats = out
+    got = st.result()
+    assert got["count"] == ref["count"]
+    assert abs(got["mean"] - ref["mean"]) <= 2e-6 * abs(ref["mean"]) + 1e-7
+    assert abs(got["std"] - ref["std"]) <= 2e-6 * ref["std"]
+    # the features it can also return are the contract kernel's (un-normalised, zero padded)
+    want = plan.fx_contract(torch.stack(wavs[:2]).cuda(), 0.0, 0.5, 1024, do_normalize=False)
+    assert torch.equal(feats, want) and float(feats[:, 98:].abs().max()) == 0.0
+    # the command-line drop-in on float32 WAV files listed in train_x_fold1.npy
+    import struct
+
+    paths = []
+    for i, w in enumerate(wavs):
+        p = tmp_path / f"s{i}.wav"
+        b = w.numpy().astype("<f4")
+        with open(p, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", 36 + b.nbytes) + b"WAVE")
+            f.write(b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 16000, 64000, 4, 32))
+            f.write(b"data" + struct.pack("<I", b.nbytes) + b.tobytes())
+        paths.append(str(p))
+    np.save(tmp_path / "train_x_fold1.npy", np.array(paths))
+    np.save(tmp_path / "train_x_fold2.npy", np.array(paths[:2]))
+    stats.main(["--data-dir", str(tmp_path), "--output-dir", str(tmp_path / "out"), "--folds", "2", "--batch-size", "4"])
+    per_fold = json.load(open(tmp_path / "out" / "stats_per_fold.json"))
+    assert [d["fold"] for d in per_fold] == [1, 2] and per_fold[0]["count"] == ref["count"]
+    assert abs(per_fold[0]["mean"] - ref["mean"]) <= 2e-6 * abs(ref["mean"]) + 1e-7
+    assert abs(per_fold[0]["std"] - ref["std"]) <= 2e-6 * ref["std"]
+    agg = json.load(open(tmp_path / "out" / "stats_aggregate.json"))
+    assert agg == stats.aggregate_stats(per_fold)
+    assert os.path.exists(tmp_path / "out" / "stats_all.npz")

@@ -213,3 +213,18 @@ def test_batch_plan_is_made_once_and_broadcast(tmp_path):
     # ranks hold the SAME plan: disjoint shards whose union is exactly rank 0's todo list
     assert got["before"] == sorted(pids)
     assert sorted(got[0] + got[1]) == ["22", "33", "44"] and not set(got[0]) & set(got[1])
+
+
+def test_stats_aggregate_matches_the_reference_function(golden_dir):
+    """stats.aggregate_stats / stats.finish against tests/golden/stats_golden.json, produced by EXECUTING the reference's
+    own aggregate_stats (utils/compute_ast_normalization_stats.py:98-113) and its accumulation loop (:62-95)."""
+    from zenker_audio_detection_b200 import stats
+
+    g = json.load(open(os.path.join(golden_dir, "stats_golden.json")))
+    agg = stats.aggregate_stats(g["per_fold"])
+    assert agg.keys() == g["aggregate"].keys() and agg["total_count"] == g["aggregate"]["total_count"]
+    assert agg["mean"] == g["aggregate"]["mean"] and agg["std"] == g["aggregate"]["std"]  # same float64 arithmetic
+    assert stats.aggregate_stats([]) == {"mean": 0.0, "std": 0.0, "total_count": 0}
+    assert stats.finish(0.0, 0.0, 0) == {"mean": 0.0, "std": 0.0, "count": 0}
+    f = stats.finish(10.0, 30.0, 4)
+    assert f["mean"] == 2.5 and abs(f["std"] - ((30.0 / 4 - 6.25) * 4 / 3) ** 0.5) < 1e-15

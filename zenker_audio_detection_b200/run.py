@@ -15,6 +15,19 @@ def main(argv=None) -> None:
 
     patch_transformers()
     patch_torchaudio()  # WAV decoding without TorchCodec (ref:54, ref:132)
+    # The scripts threshold the returned scores on the host (ref:312-320, ref:333), so the drop-in models must know the
+    # decision points to re-check around (model.py): pick the threshold flags out of the script's own command line.
+    thr = []
+    for flag in ("--stage1-threshold", "--stage2-threshold", "--stage1-forward-min-prob"):
+        for i, a in enumerate(argv):
+            v = argv[i + 1] if a == flag and i + 1 < len(argv) else (a.split("=", 1)[1] if a.startswith(flag + "=") else None)
+            if v is not None:
+                try:
+                    thr.append(str(float(v)))
+                except ValueError:
+                    pass
+    if thr and "ZK_RECHECK_THRESHOLDS" not in os.environ:
+        os.environ["ZK_RECHECK_THRESHOLDS"] = ",".join(["0.5"] + thr)
     script = argv[0]
     sys.argv = argv
     sys.path.insert(0, os.path.dirname(os.path.abspath(script)))
