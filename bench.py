@@ -216,7 +216,12 @@ def build_pipeline(args, device):
     sd1, sd2 = synth.random_state_dict(11), synth.random_state_dict(22)
     m1 = ZenkerASTForAudioClassification({"max_length": 1024}, sd1).to(device)
     m2 = ZenkerASTForAudioClassification({"max_length": 1024}, sd2).to(device)
-    return TwoStagePipeline(m1, fx1, m2, fx2, batch_size=args.batch_size), sd1
+    kw = {}
+    if getattr(args, "recheck_batch", None):
+        kw["recheck_batch"] = args.recheck_batch
+    if getattr(args, "recheck_eps", None) is not None:
+        kw["recheck_eps"] = args.recheck_eps
+    return TwoStagePipeline(m1, fx1, m2, fx2, batch_size=args.batch_size, **kw), sd1
 
 
 def calibrate_gate(pipe, sd1, wave_dev, fraction, device):
@@ -727,6 +732,8 @@ def main():
     ap.add_argument("--stage2-fraction", type=float, default=0.3)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--skip-library", action="store_true", help="skip the library-kernel / HF-on-B200 comparisons")
+    ap.add_argument("--recheck-batch", type=int, default=None, help="windows per launch of the re-check forward (default 16)")
+    ap.add_argument("--recheck-eps", type=float, default=None, help="half-width of the re-check band in logit units (default by operand format)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--pool", type=int, default=64, help="cfg4: recordings in the fixed pool (2 per patient)")
     ap.add_argument("--pool-seconds", default="90,150", help="cfg4: recording lengths are U(lo,hi) seconds")

@@ -104,3 +104,28 @@ def test_attention_split_window_independence():
     both = ops.attention_split(qkv, 2, T)
     alone = ops.attention_split(qkv[:T].contiguous(), 1, T)
     assert torch.equal(both[:T], alone)
+
+
+def test_attention_split_mma_variant_still_agrees():
+    """ZK_SPLIT_ATTN=mma selects the warp-level mma.sync kernel instead of the tcgen05 one (the switch is read once per
+    process, hence the subprocess): both must give float64-class results on the same inputs."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from zenker_audio_detection_b200 import ops\n"
+        "g = torch.Generator(device='cuda').manual_seed(5)\n"
+        "B, T = 2, 333\n"
+        "qkv = torch.randn(B * T, 2304, device='cuda', generator=g); qkv[:, :1536] *= 2.0\n"
+        "out = ops.attention_split(ops.split_f16(qkv), B, T)\n"
+        "val = out[:, :768].double() + out[:, 768:].double()\n"
+        "q, k, v = (qkv[:, i * 768:(i + 1) * 768].double().view(B, T, 12, 64).transpose(1, 2) for i in range(3))\n"
+        "ref = (torch.softmax((q @ k.transpose(2, 3)) * 0.125, -1) @ v).transpose(1, 2).reshape(B * T, 768)\n"
+        "err = (val - ref).abs().max().item(); print(err); assert err < 5e-6, err\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for variant in ("mma", "tc"):
+        env = dict(os.environ, ZK_SPLIT_ATTN=variant)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, (variant, r.stdout[-500:], r.stderr[-1500:])
