@@ -223,7 +223,9 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
   tmem_st_wait();
 }
 
-template <int POLY, int FMT>
+// TRACE = false is the production instantiation: the timeline hooks (and the pointer arithmetic / flag registers they
+// keep alive across every key block: ~60 of the ~100 instructions of block entry + exit) are compiled out.
+template <int POLY, int FMT, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int tokens,
             int num_items, int qpairs, int stagger, int half_keys, long long* trace, int trace_items) {
@@ -246,10 +248,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
   const int my_items = ((int)blockIdx.x < num_items) ? (num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // optional timeline capture (zk_attention_trace): 128 slots per CTA, first item of each CTA
   // trace_items: record only the end of every work item (slots 8 + it for tile A, 68 + it for tile B, it < 60)
-  long long* tr_it = (trace && trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
-  long long* tr = (trace && !trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
-  if (tr_it && threadIdx.x == 0) tr_it[1] = clock64();
-  if (tr && threadIdx.x == 0) {
+  long long* tr_it = (TRACE && trace && trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
+  long long* tr = (TRACE && trace && !trace_items && blockIdx.x < 512) ? trace + (long long)blockIdx.x * 128 : nullptr;
+  if (TRACE && tr_it && threadIdx.x == 0) tr_it[1] = clock64();
+  if (TRACE && tr && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tr[0] = smid;
@@ -341,7 +343,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
           umma_commit(&s_full[t]);
           // the Q buffer of the item is dead once the last S of both tiles has executed (barrier count 2)
           if (j == (uint32_t)nkv - 1) umma_commit(&q_empty[it & 1]);
-          if (tr && t == 0 && g < 15) tr[8 + g * 8 + 5] = clock64();
+          if (TRACE && tr && t == 0 && g < 15) tr[8 + g * 8 + 5] = clock64();
         }
         __syncwarp();
       };
@@ -370,7 +372,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
           }
           umma_commit(&pv_done[t]);
           umma_commit(&kv_empty[g % KV_STAGES]);  // K_g / V_g are dead once both tiles' P V have executed (count 2)
-          if (tr && t == 0 && g < 15) tr[8 + g * 8 + 6] = clock64();
+          if (TRACE && tr && t == 0 && g < 15) tr[8 + g * 8 + 6] = clock64();
         }
         __syncwarp();
       }
@@ -383,7 +385,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t t_s = t_lane + TM_S + t * BKV, t_o = t_lane + TM_O + t * D, t_p = t_lane + TM_P + t * 64;
-    const bool tracer = tr && warp == 4 && lane == 0;
+    const bool tracer = TRACE && tr && warp == 4 && lane == 0;
     SoftmaxState st;
     st.m = -INFINITY;
     st.l2a = make_float2(0.f, 0.f);
@@ -394,7 +396,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
       item_coords(it, b, h, qb);
       const bool row_valid = (qb * QTILES + t) * BQ + row < tokens;
       for (int j = 0; j < nkv; ++j, ++n) {
-        long long* trj = (tracer && n < 15) ? tr + 8 + n * 8 : nullptr;
+        long long* trj = (TRACE && tracer && n < 15) ? tr + 8 + n * 8 : nullptr;
         if (trj) trj[0] = clock64();
         mbar_wait(&s_full[t], n & 1);
         tc_fence_after();
@@ -419,7 +421,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         tc_fence_before();
         mbar_arrive(&p_full[t]);
         if (trj) trj[2] = clock64();
-        if (tr && warp == 8 && lane == 0 && n < 15) tr[8 + n * 8 + 4] = clock64();  // tile B: P published
+        if (TRACE && tr && warp == 8 && lane == 0 && n < 15) tr[8 + n * 8 + 4] = clock64();  // tile B: P published
       }
       // epilogue of the item: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store per tile (rows beyond the
       // window's last token are clipped by the 3-D tensor map).  The next item's first P V (accumulate = 0) is only
@@ -449,8 +451,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         tma_store_3d(&tm_out, stg, h * D, (qb * QTILES + t) * BQ, b);
         bulk_commit();
       }
-      if (tracer && it == 0) tr[2] = clock64();
-      if (tr_it && quarter == 0 && lane == 0 && it < 60) tr_it[(t ? 68 : 8) + it] = clock64();
+      if (TRACE && tracer && it == 0) tr[2] = clock64();
+      if (TRACE && tr_it && quarter == 0 && lane == 0 && it < 60) tr_it[(t ? 68 : 8) + it] = clock64();
     }
     if ((warp & 3) == 0 && lane == 0) bulk_wait0();  // every output tile has landed before the CTA retires
   }
@@ -462,17 +464,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
 }  // namespace attn
 
-template <int POLY, int FMT>
-static int launch_attn(const CUtensorMap& tm, const CUtensorMap& o, int grid, int tokens, int items, int qpairs, int stagger,
+template <int POLY, int FMT, bool TRACE>
+static int launch_attn_t(const CUtensorMap& tm, const CUtensorMap& o, int grid, int tokens, int items, int qpairs, int stagger,
                        int half_keys, long long* trace, int trace_items, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn::attn_kernel<POLY, FMT>), attn::SMEM_BYTES, &attr_done))
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn::attn_kernel<POLY, FMT, TRACE>), attn::SMEM_BYTES, &attr_done))
     return rc;
   ProfScope prof(ZK_K_ATTENTION, stream);
-  attn::attn_kernel<POLY, FMT><<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, o, tokens, items, qpairs, stagger,
+  attn::attn_kernel<POLY, FMT, TRACE><<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, o, tokens, items, qpairs, stagger,
                                                                                half_keys, trace, trace_items);
   ZK_LAUNCH_CHECK("attn_kernel");
   return 0;
+}
+
+template <int POLY, int FMT>
+static int launch_attn(const CUtensorMap& tm, const CUtensorMap& o, int grid, int tokens, int items, int qpairs, int stagger,
+                       int half_keys, long long* trace, int trace_items, cudaStream_t stream) {
+  // the traced build only exists for the default exp2 split (scripts/attn_trace.py, scripts/attn_items.py)
+  if (trace && POLY == 1)
+    return launch_attn_t<1, FMT, true>(tm, o, grid, tokens, items, qpairs, stagger, half_keys, trace, trace_items, stream);
+  return launch_attn_t<POLY, FMT, false>(tm, o, grid, tokens, items, qpairs, stagger, half_keys, nullptr, 0, stream);
 }
 
 int attention16_impl(const void* qkv, void* out, int batch, int tokens, int fmt, long long* trace, cudaStream_t stream) {
