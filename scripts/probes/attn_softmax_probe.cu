@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128 + NSOFT * 32, 1) softmax_probe_kernel(int 
     st.l2b = make_float2(0.f, 0.f);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
-      softmax_block<false, false, POLY, FMT, W>(0, W, true, t_s, t_o, t_p, &bars[0], &bars[1], st, nullptr);
+      softmax_block<false, false, POLY, FMT, W>(0, W, true, t_s, t_o, t_p, smem_u32(&bars[0]), smem_u32(&bars[1]), st, nullptr);
       tc_fence_before();
       mbar_arrive(&bars[0]);
     }

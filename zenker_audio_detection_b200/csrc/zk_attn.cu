@@ -124,7 +124,7 @@ struct SoftmaxState {
 // 1214 leaves 62) only takes the lower half of S, writes the lower half of P, and the issuer shortens P V to W keys.
 template <bool RAGGED, bool FIRST, int POLY, int FMT, int W = 128>
 __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_valid, uint32_t t_s, uint32_t t_o, uint32_t t_p,
-                                              uint64_t* s_free, uint64_t* pv_done, SoftmaxState& st, long long* trj) {
+                                              uint32_t s_free, uint32_t pv_done, SoftmaxState& st, long long* trj) {
   uint32_t s[128];
   static_assert(W == 64 || W == 128, "key columns per block");
   tmem_ld32_at<0>(t_s, s);
@@ -135,12 +135,17 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
   }
   tmem_ld_wait();
   tc_fence_before();
-  mbar_arrive(s_free);  // the score buffer may be overwritten by S(j+1) from here on
+  mbar_arrive_a(s_free);  // the score buffer may be overwritten by S(j+1) from here on
   if (trj) trj[3] = clock64();
-  if (RAGGED) {
+  if (RAGGED) {  // keys >= kmax -> -inf; kmax is uniform, so only the group of 8 that straddles it pays the compares
 #pragma unroll
-    for (int i = 0; i < W; ++i)
-      if (i >= kmax) s[i] = 0xff800000u;  // -inf
+    for (int i0 = 0; i0 < W; i0 += 8) {
+      if (i0 + 8 > kmax) {
+#pragma unroll
+        for (int i = i0; i < i0 + 8; ++i)
+          if (i >= kmax) s[i] = 0xff800000u;
+      }
+    }
   }
   if (FIRST) {
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -191,7 +196,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
         }
       }
       if (c == 0 && pass == 0 && n > 0) {
-        mbar_wait(pv_done, (n - 1) & 1);  // the P buffer is free (and O final up to block j-1) once P(j-1) V(j-1) is done
+        mbar_wait_a(pv_done, (n - 1) & 1);  // the P buffer is free (and O final up to block j-1) once P(j-1) V(j-1) is done
         tc_fence_after();
       }
       tmem_st16(t_p + c * 16, pk);
@@ -386,6 +391,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t t_s = t_lane + TM_S + t * BKV, t_o = t_lane + TM_O + t * D, t_p = t_lane + TM_P + t * 64;
     const bool tracer = TRACE && tr && warp == 4 && lane == 0;
+    // this tile's four barriers as 32-bit shared addresses held in registers (see smem_addr_keep)
+    const uint32_t a_s_full = smem_addr_keep(&s_full[t]), a_s_free = smem_addr_keep(&s_free[t]);
+    const uint32_t a_p_full = smem_addr_keep(&p_full[t]), a_pv_done = smem_addr_keep(&pv_done[t]);
     SoftmaxState st;
     st.m = -INFINITY;
     st.l2a = make_float2(0.f, 0.f);
@@ -398,35 +406,35 @@ attn_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
       for (int j = 0; j < nkv; ++j, ++n) {
         long long* trj = (TRACE && tracer && n < 15) ? tr + 8 + n * 8 : nullptr;
         if (trj) trj[0] = clock64();
-        mbar_wait(&s_full[t], n & 1);
+        mbar_wait_a(a_s_full, n & 1);
         tc_fence_after();
         if (trj) trj[1] = clock64();
         const int kmax = tokens - j * BKV;  // keys [0, kmax) of this block are valid; only the last block is ragged
         if (kmax <= half_keys) {
           if (j == 0)
-            softmax_block<true, true, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, true, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
           else
-            softmax_block<true, false, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, false, POLY, FMT, 64>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
         } else if (kmax < BKV) {
           if (j == 0)
-            softmax_block<true, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
           else
-            softmax_block<true, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<true, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
         } else {
           if (j == 0)
-            softmax_block<false, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, true, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
           else
-            softmax_block<false, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, &s_free[t], &pv_done[t], st, trj);
+            softmax_block<false, false, POLY, FMT>(n, kmax, row_valid, t_s, t_o, t_p, a_s_free, a_pv_done, st, trj);
         }
         tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        mbar_arrive_a(a_p_full);
         if (trj) trj[2] = clock64();
         if (TRACE && tr && warp == 8 && lane == 0 && n < 15) tr[8 + n * 8 + 4] = clock64();  // tile B: P published
       }
       // epilogue of the item: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store per tile (rows beyond the
       // window's last token are clipped by the 3-D tensor map).  The next item's first P V (accumulate = 0) is only
       // issued after this thread has published its next P, i.e. after these TMEM reads.
-      mbar_wait(&pv_done[t], (n - 1) & 1);
+      mbar_wait_a(a_pv_done, (n - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / ((st.l2a.x + st.l2a.y) + (st.l2b.x + st.l2b.y));
       uint32_t r[64];

@@ -135,6 +135,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same on a 32-bit shared-memory address the caller computed ONCE (smem_addr_keep): with a generic pointer the
+// compiler re-derives the address (thread-id arithmetic, S2UR of the shared window, a dependent ULEA: ~12 instructions
+// and two scoreboard waits) in front of every barrier operation of a register-starved loop.
+__device__ __forceinline__ uint32_t smem_addr_keep(const void* p) {
+  uint32_t a = smem_u32(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // opaque: cannot be rematerialised, stays in its register
+  return a;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;
+  long long t0 = clock64();
+  uint32_t n = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) return;
+    if ((++n & 0x3ff) == 0 && clock64() - t0 > 8000000000LL) {
+      printf("zk: mbarrier timeout block=(%d,%d,%d) thread=%d bar=smem+%u parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
