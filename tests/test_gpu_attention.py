@@ -67,6 +67,31 @@ def test_attention_fp16(B, T, scale):
     assert rel <= 1.5e-3, rel
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("key", [256, 257, 258, 300, 391, 1213])
+def test_attention_one_key_far_above_the_running_maximum(key, dtype):
+    """A key in a LATER block whose score exceeds everything before it by hundreds of units: exp2 against the stale
+    maximum overflows (MUFU.EX2 saturates to inf, the FMA-pipe polynomial wraps around), so the rescale trigger -- the
+    block's row sum plus the maximum over the polynomial's own arguments -- must fire whichever slot the key falls
+    into (256 / 257: polynomial pair, 258 / 300: MUFU pair, 391: odd position, 1213: the ragged half block)."""
+    from zenker_audio_detection_b200 import ops
+
+    T = 1214
+    g = torch.Generator(device="cuda").manual_seed(key)
+    qkv = torch.randn(T, 2304, device="cuda", generator=g) * 0.5
+    qkv[:, :768] = qkv[:, :768].abs()                  # q >= 0 ...
+    qkv[key, 768:1536] = 24.0                          # ... so this key scores ~ 24 * 64 * E|q| / 8 = 77 x the others
+    qkv = qkv.to(dtype)
+    out = ops.attention(qkv, 1, T)
+    ref = _ref(qkv, 1, T)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= (5e-3 if dtype == torch.float16 else 3.5e-2), err
+    # every row is (all but) one-hot on `key`
+    v = qkv[key, 1536:].float()
+    assert (out.float() - v).abs().max().item() <= 0.1
+
+
 def _ref64(qkv32, B, T):
     q, k, v = (qkv32[:, i * 768:(i + 1) * 768].double().view(B, T, 12, 64).transpose(1, 2) for i in range(3))
     s = (q @ k.transpose(2, 3)) * 0.125

@@ -46,6 +46,8 @@ constexpr uint32_t TMEM_COLS = 512, TM_S = 0, TM_O = 256, TM_P = 384;
 template <int FMT>
 constexpr float rescale_tau() { return FMT == FMT_F16 ? 15.0f : 24.0f; }
 constexpr float SCALE_LOG2E = 0.125f * 1.44269504088896340736f;
+// the rescale trigger of the online softmax: true = the block's row sum (free), false = the block's maximum (FMNMX3)
+constexpr bool SUM_TEST = true;
 constexpr int REGS_SOFTMAX = 216, REGS_OTHER = 56;
 static_assert(128 * REGS_OTHER + 256 * REGS_SOFTMAX <= 65536, "register file");
 
@@ -167,7 +169,7 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
   for (int pass = 0;; ++pass) {
     // p = exp2(s * c - m * c), row sum, bf16 pack; P goes to TMEM as the A operand of P V (column i = keys 2i, 2i+1)
     const float2 mb2 = make_float2(-st.m * SCALE_LOG2E, -st.m * SCALE_LOG2E);
-    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY, mxp = -INFINITY;
     lba = make_float2(0.f, 0.f);
     lbb = make_float2(0.f, 0.f);
 #pragma unroll
@@ -181,11 +183,15 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
         // pairs are numbered i/2; out of every four, the first POLY go to the FMA pipe
         const float2 pa = (((i >> 1) & 3) < POLY) ? exp2_poly2(xa) : make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
         const float2 pb = ((((i >> 1) + 1) & 3) < POLY) ? exp2_poly2(xb) : make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+        // the FMA-pipe exp2 wraps around for arguments past 2^7 (its exponent patch is an integer add) instead of
+        // saturating like MUFU.EX2, so the row-sum test below cannot see such an element: track their arguments
+        if (SUM_TEST && !FIRST && (((i >> 1) & 3) < POLY)) mxp = fmax3(mxp, xa.x, xa.y);
+        if (SUM_TEST && !FIRST && ((((i >> 1) + 1) & 3) < POLY)) mxp = fmax3(mxp, xb.x, xb.y);
         lba = fadd2(lba, pa);
         lbb = fadd2(lbb, pb);
         pk[i >> 1] = pack16<FMT>(pa.x, pa.y);
         pk[(i >> 1) + 1] = pack16<FMT>(pb.x, pb.y);
-        if (!FIRST) {
+        if (!FIRST && !SUM_TEST) {
           if (i & 4) {
             mx2 = fmax3(mx2, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
             mx3 = fmax3(mx3, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
@@ -202,12 +208,31 @@ __device__ __forceinline__ void softmax_block(uint32_t n, int kmax, bool row_val
       tmem_st16(t_p + c * 16, pk);
     }
     if (FIRST || pass == 1) break;
-    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     // Only rows that are real queries of this window vote, and only rows that exceed the threshold themselves move
     // their maximum: a row's result must not depend on what else shares its warp (the rows past the last token of a
     // window hold the NEXT window's queries, i.e. they change with the batch composition).
-    const bool exceed = row_valid && (mx - st.m) * SCALE_LOG2E > rescale_tau<FMT>();
-    if (!__any_sync(0xffffffffu, exceed)) break;
+    bool exceed;
+    if (SUM_TEST) {
+      // The block's row sum is computed anyway and bounds every p of the row from above: as long as it stays below
+      // 2^tau no element left the operand format's range and the block maximum is never needed (64 FMNMX3 per block
+      // that only the rare path below pays; the FMA-pipe elements keep a maximum of their own, see above).  A NaN /
+      // inf sum fails the comparison and takes the rare path too.
+      const float lsum = (lba.x + lba.y) + (lbb.x + lbb.y);
+      exceed = row_valid && (!(lsum <= exp2f(rescale_tau<FMT>())) || mxp > rescale_tau<FMT>());
+      if (!__any_sync(0xffffffffu, exceed)) break;
+#pragma unroll
+      for (int i = 0; i < W; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+    }
+    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    if (!SUM_TEST) {
+      exceed = row_valid && (mx - st.m) * SCALE_LOG2E > rescale_tau<FMT>();
+      if (!__any_sync(0xffffffffu, exceed)) break;
+    }
     // rare: advance the running maximum, rescale the accumulator in TMEM (whole warp, tcgen05 is collective), redo
     const float mn = exceed ? mx : st.m;
     const float alpha = fast_exp2((st.m - mn) * SCALE_LOG2E);
