@@ -783,7 +783,7 @@ def main():
     ap.add_argument("--stage2-fraction", type=float, default=0.3)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--skip-library", action="store_true", help="skip the library-kernel / HF-on-B200 comparisons")
-    ap.add_argument("--recheck-batch", type=int, default=None, help="windows per launch of the re-check forward (default 16)")
+    ap.add_argument("--recheck-batch", type=int, default=None, help="windows per launch of the re-check forward (default 62)")
     ap.add_argument("--recheck-eps", type=float, default=None, help="half-width of the re-check band in logit units (default by operand format)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--pool", type=int, default=64, help="cfg4: recordings in the fixed pool (2 per patient)")

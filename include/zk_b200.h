@@ -211,7 +211,7 @@ int zk_sum_sumsq_f64(const float* d_x, int64_t n, double* d_acc, zk_stream_t str
  * ------------------------------------------------------------------------------------------ */
 typedef struct zk_cascade_params {
   int32_t batch_size;      /* windows per launch of the FAST forward (128) */
-  int32_t recheck_batch;   /* windows per launch of the RECHECK forward (16) */
+  int32_t recheck_batch;   /* windows per launch of the RECHECK forward (62: 4.0 waves of 256-row CTA-pair tiles) */
   int32_t window_samples;  /* int(window_sec * 16000), ref:63 */
   int32_t hop_samples;     /* int(hop_sec * 16000), ref:64 */
   float mean1, std1;       /* Stage-1 extractor statistics (HF:feature_extraction...:155-156) */

@@ -418,7 +418,7 @@ class AstModel:
                   "zk_model_forward")
         return (logits, hidden) if return_hidden else logits
 
-    def recheck_features(self, feats: torch.Tensor, logits: torch.Tensor, margins, eps: float, chunk: int = 16) -> int:
+    def recheck_features(self, feats: torch.Tensor, logits: torch.Tensor, margins, eps: float, chunk: int = 62) -> int:
         """Decision re-check on the contract path: rows of ``logits`` whose margin is within ``eps`` of a decision point
         are recomputed at ``PRECISION_RECHECK`` from the same feature rows and overwritten in place.  Returns how many."""
         if eps <= 0 or not len(margins) or logits.shape[0] == 0:

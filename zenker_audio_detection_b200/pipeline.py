@@ -56,7 +56,7 @@ class TwoStagePipeline:
                  window_sec: float = 1.0, hop_sec: float = 0.5, stage1_threshold: float = 0.5,
                  stage2_threshold: float = 0.5, stage1_forward_min_prob: Optional[float] = None,
                  stage2_argmax: bool = False, device: Optional[Union[str, torch.device]] = None,
-                 recheck_eps: Optional[float] = None, recheck_batch: int = 16):
+                 recheck_eps: Optional[float] = None, recheck_batch: int = 62):
         if not torch.cuda.is_available():
             raise ZkError("TwoStagePipeline needs a B200; there is no CPU path")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
