@@ -1,9 +1,9 @@
 // Audio front end for sm_100a: polyphase resampler and the Kaldi-compatible log-mel filterbank.
 //
-// fbank kernel: one persistent CTA per SM (12 warps) walks tiles of 48 consecutive frames.  The 7920 samples a tile
+// fbank kernel: one persistent CTA per SM (14 warps) walks tiles of 56 consecutive frames.  The 9200 samples a tile
 // needs are staged into shared memory with ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) that
 // completes on an mbarrier; the copy of tile i+1 is issued before tile i is processed (double buffer), so HBM reads are
-// contiguous 31 KiB bursts and each sample is fetched from HBM once although frames overlap 2.5x.  A warp owns four
+// contiguous 36 KiB bursts and each sample is fetched from HBM once although frames overlap 2.5x.  A warp owns four
 // frames: each 16-lane half processes TWO frames at once, packed in the two halves of f32x2 registers, so every fp32
 // operation of the pipeline is a packed FADD2 / FMUL2 / FFMA2 (the fp32 peak of sm_100 is only reachable through the
 // packed forms, and at ~14 flop/B this kernel sits at the fp32 ridge, not the HBM one).  DC removal, pre-emphasis and
@@ -37,8 +37,8 @@ using namespace fb;
 typedef cpxv<float2> cpx2;
 static_assert(sizeof(cpx2) == 16, "packed complex pair is one 16-byte shared-memory element");
 
-constexpr int WARPS = 12, THREADS = WARPS * 32, TILE_FRAMES = 4 * WARPS;
-constexpr int TILE_SAMPLES = (TILE_FRAMES - 1) * SHIFT + FRAME;  // 7920
+constexpr int WARPS = 14, THREADS = WARPS * 32, TILE_FRAMES = 4 * WARPS;
+constexpr int TILE_SAMPLES = (TILE_FRAMES - 1) * SHIFT + FRAME;  // 9200
 constexpr int UNIT_SCRATCH = 16 * TPITCH * 4;                    // floats per 16-lane half: the transpose buffer
 static_assert(UNIT_SCRATCH >= 2 * 512, "exchange + power buffers alias the transpose buffer");
 // shared memory carve-up (floats)
