@@ -552,6 +552,15 @@ def run_ours(args):
                 ach = amount / (cms * 1e-3) / 1e9
                 row.update({"bound": "hbm", "achieved": ach, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": ach / peaks["hbm_gbs"], "bytes": amount})
         table[cls] = row
+    if "gemm_out" in table and "frac" in table["gemm_out"]:
+        # the out-projection is the one GEMM whose binding roof is HBM, not the tensor pipe: per output element it reads
+        # 2 B of A, read-modify-writes the fp32 residual (8 B) and does only 2 x 768 flops (ncu: 0.72 GB read + 0.42 GB
+        # written per 128-window launch, profiles/r02_gemm.csv)
+        layers = 12 if full_last else FULL_LAYERS
+        nbytes = (2.0 + 8.0) * windows_fast * TOKENS * HID * layers
+        gbs = nbytes / (prof["gemm_out"][0] * 1e-3) / 1e9
+        table["gemm_out"]["hbm"] = {"achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+                                    "bytes": nbytes, "note": "algorithmic: fp16 A once + fp32 residual read and write; this is the binding roof"}
     re_rank = re_p // max(1, world)
     if "recheck" in table and prof["recheck"][0] > 0:
         ach = re_rank * 3 * GFLOP_PER_WINDOW / 1e3 / (prof["recheck"][0] * 1e-3)
