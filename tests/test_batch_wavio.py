@@ -110,13 +110,53 @@ def test_ids_thresholds_and_plan(tmp_path, capsys):
     (out / "301_2stage.json").write_text("{}")
     args = batch.build_arg_parser().parse_args(["--fold", "3", "--ids-root", str(ids), "--long-audio-root", str(root),
                                                 "--output-dir", str(out), "--dry-run"])
-    plans = [batch.plan_patients(args, r, 2)[0] for r in range(2)]
+    todo, _ = batch.global_plan(args)
+    plans = [batch.shard_plan(todo, r, 2) for r in range(2)]
     assert sorted(pid for pl in plans for pid, _ in pl) == ["224"]  # 301 exists -> skipped, 17 has one file -> error
     assert batch.run(args, 0, 1) == 0
     printed = capsys.readouterr().out
     assert "[SKIP] 301" in printed and "[ERROR] patient 9017" in printed and "[RUN] rank 0: 224" in printed
     args.force = True
     assert sorted(pid for pid, _ in batch.plan_patients(args, 0, 1)[0]) == ["224", "301"]
+
+
+def _plan_worker(rank, world, port, argv, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    args = batch.build_arg_parser().parse_args(argv)
+    # rank 1's own view of the work differs from rank 0's (as if it had looked at the output directory at another
+    # time): planning on its own it would also take 224, whose result file exists
+    args.force = rank == 1
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine, _ = batch.plan_patients(args, rank, world)
+    q.put((rank, [pid for pid, _ in mine]))
+    dist.destroy_process_group()
+
+
+def test_plan_is_made_on_rank_0_and_broadcast(tmp_path):
+    """every rank must shard the SAME plan (gloo, world size 2): the union of the shares is rank 0's plan
+    and no patient is dropped or duplicated, whatever the other ranks see in the output directory."""
+    import torch.multiprocessing as mp
+
+    root, ids = _tree(tmp_path)
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "224_2stage.json").write_text("{}")
+    argv = ["--fold", "3", "--ids-root", str(ids), "--long-audio-root", str(root), "--output-dir", str(out), "--dry-run"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, argv, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    shares = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = sorted(shares[0] + shares[1])
+    assert len(got) == len(set(got))                       # nobody is processed twice
+    assert got == ["301"], shares                          # rank 0's plan (224 skipped), not rank 1's own view
 
 
 def test_batch_flags_are_the_launchers():

@@ -177,8 +177,6 @@ def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str
     With more than one rank the plan is made by rank 0 alone and broadcast: a rank that started late would otherwise see
     result files an early rank has already written, skip those patients, shard a DIFFERENT list and drop or duplicate
     work.  The exchange goes over a gloo group (host objects); ranks then shard the identical list longest-first."""
-    from .dist import shard_recordings
-
     if world > 1:
         import torch.distributed as dist
 
@@ -189,8 +187,16 @@ def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str
         todo, log = box[0]
     else:
         todo, log = global_plan(args)
+    return shard_plan(todo, rank, world), log
+
+
+def shard_plan(todo, rank: int, world: int) -> List[Tuple[str, List[str]]]:
+    """Rank ``rank``'s share of one global plan ``[(patient, files, bytes)]``: patients dealt longest-first
+    (``dist.shard_recordings`` on the byte counts), so every rank derives the same partition from the same list."""
+    from .dist import shard_recordings
+
     mine = shard_recordings([b for _, _, b in todo], world)[rank] if todo else []
-    return [(todo[i][0], todo[i][1]) for i in mine], log
+    return [(todo[i][0], todo[i][1]) for i in mine]
 
 
 def run(args, rank: int = 0, world: int = 1) -> int:
