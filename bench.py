@@ -561,6 +561,16 @@ def run_ours(args):
         gbs = nbytes / (prof["gemm_out"][0] * 1e-3) / 1e9
         table["gemm_out"]["hbm"] = {"achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
                                     "bytes": nbytes, "note": "algorithmic: fp16 A once + fp32 residual read and write; this is the binding roof"}
+    if "attention" in table and "frac" in table["attention"]:
+        # at head_dim 64 the exponentials, not the MMAs, are the roof of fused attention: one exp2 per score against the
+        # 16 MUFU.EX2 lanes per clock per SM (measured: scripts/attn_probe.py), at the SM clock this run actually had
+        layers = 12 if full_last else FULL_LAYERS
+        exps = float(windows_fast) * layers * 12 * TOKENS * TOKENS
+        mhz = float(clocks.get("sm_mhz") or 0.0) if isinstance(clocks, dict) else 0.0
+        if mhz > 0:
+            rate = exps / (prof["attention"][0] * 1e-3) / (torch.cuda.get_device_properties(device).multi_processor_count * mhz * 1e6)
+            table["attention"]["mufu"] = {"exp_per_clk_per_sm": rate, "ceiling": 16.0, "frac": rate / 16.0, "sm_mhz": mhz,
+                                          "note": "useful exponentials only (padded rows / keys excluded); a quarter of them run on the FMA pipe instead"}
     re_rank = re_p // max(1, world)
     if "recheck" in table and prof["recheck"][0] > 0:
         ach = re_rank * 3 * GFLOP_PER_WINDOW / 1e3 / (prof["recheck"][0] * 1e-3)
