@@ -49,7 +49,19 @@ def main():
         del w, o
     qkv = (torch.randn(M, 2304, device="cuda", generator=g)).to(DT)
     qkv[:, :1536] *= 2.0
-    ms = timeit(lambda: ops.attention(qkv, B, T))
+    # ours and torch SDPA alternate (ours, sdpa, sdpa, ours; 50 back-to-back launches each) so that both see the same
+    # clock: a kernel timed right after the GEMM loops above runs at the power-capped clock, one timed later does not
+    qq, kk, vv = (qkv[:, i * 768:(i + 1) * 768].view(B, T, 12, 64).transpose(1, 2) for i in range(3))
+    t_ours, t_sdpa, sd = [], [], None
+    for which in ("ours", "sdpa", "sdpa", "ours"):
+        try:
+            if which == "ours":
+                t_ours.append(timeit(lambda: ops.attention(qkv, B, T), iters=50))
+            else:
+                t_sdpa.append(timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv), iters=50))
+        except Exception as e:  # noqa: BLE001
+            sd = str(e)
+    ms = sum(t_ours) / len(t_ours)
     tf = 4.0 * B * 12 * T * T * 64 / ms / 1e9
     out["attention"] = {"ms": ms, "tflops": tf, "frac_sustained": tf / PEAKS["bf16_tflops_sustained"], "poly": os.environ.get("ZK_ATTN_POLY", "default")}
     # accuracy of the attention variant on a small case
@@ -59,14 +71,9 @@ def main():
     ref = (torch.softmax((q @ k.transpose(2, 3)) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(2 * T, 768)
     out["attention"]["max_abs_err"] = (got - ref).abs().max().item()
     out["attention"]["rel_err"] = ((got - ref).norm() / ref.norm()).item()
-    sd = ms_sdpa = None
-    try:
-        qq, kk, vv = (qkv[:, i * 768:(i + 1) * 768].view(B, T, 12, 64).transpose(1, 2) for i in range(3))
-        ms_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv))
-    except Exception as e:  # noqa: BLE001
-        sd = str(e)
+    ms_sdpa = sum(t_sdpa) / len(t_sdpa) if t_sdpa else None
     out["attention"]["torch_sdpa_ms"] = ms_sdpa
-    del qkv
+    del qkv, qq, kk, vv
     w = torch.ones(768, device="cuda")
     ms = timeit(lambda: ops.layernorm(x, w, w, 1e-12))
     out["layernorm"] = {"ms": ms, "gbs": M * 768 * 6 / ms / 1e6, "frac_hbm": M * 768 * 6 / ms / 1e6 / PEAKS["hbm_gbs"]}

@@ -14,6 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 8 -c 6 
 $CMD > gpurun_out/${tag}_plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"fbank_kernel|layernorm_kernel|decimate" -c 3 -o gpurun_out/${tag}_mem -f $CMD > gpurun_out/${tag}_ncu4.log 2>&1
 $CMD > gpurun_out/${tag}_plain5.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"attn_split|band_select|f32_to_16" -s 2 -c 4 -o gpurun_out/${tag}_split -f $CMD > gpurun_out/${tag}_ncu5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"attn_split_tc|gemm_pair_kernel<.*, 1>" -s 1 -c 5 -o gpurun_out/${tag}_split -f $CMD > gpurun_out/${tag}_ncu5.log 2>&1
 ls -la gpurun_out/ | tail -20
 tail -3 gpurun_out/${tag}_ncu2.log
