@@ -641,7 +641,7 @@ def run_ours(args):
             pipe.recheck_eps = eps
             line["secondary"]["recheck_off"] = {"windows_per_s": n_off / (ms_off / 1000.0), "ms_per_step": ms_off / args.steps,
                                                 "note": "decisions NOT guaranteed equal to the fp32 reference's in this mode"}
-        if not args.skip_library:
+        if not args.skip_library and world == 1:  # rank 0 at N = 1 only: the other ranks of a torchrun job are waiting to exit
             dt = torch.float16 if operand_format == "fp16" else torch.bfloat16
             try:
                 line["secondary"]["library_kernels"] = library_kernels(device, args.batch_size, dt)
@@ -651,7 +651,7 @@ def run_ours(args):
                 line["secondary"]["hf_on_b200"] = hf_on_b200(device)
             except Exception as e:  # noqa: BLE001
                 line["secondary"]["hf_on_b200"] = {"error": str(e)[:300]}
-        if args.cpu_seconds > 0:
+        if args.cpu_seconds > 0 and world == 1:  # the CPU baseline is reported at N = 1 only
             from oracle import glue, thirdparty
 
             audio = thirdparty.resample(synth.recording(60.0, 48000, seed=2002), 48000, 16000)
