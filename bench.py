@@ -184,8 +184,11 @@ def run_reference(args):
     windows = glue.window_audio(audio, 1.0, 0.5)
     vals = []
     total = 0.0
+    # every step is a bounded sample; its budget shrinks with the step count so that the whole run stays within ~4 minutes
+    # (at --steps 20 --warmup 5 a 20-s sample per step was a 9-minute run)
+    budget = max(3.0, min(float(args.cpu_seconds), 200.0 / max(1, args.warmup + args.steps)))
     for i in range(args.warmup + args.steps):
-        v, cores, desc, dt = cpu_reference_windows_per_s(windows, args.stage2_fraction, seconds_budget=args.cpu_seconds)
+        v, cores, desc, dt = cpu_reference_windows_per_s(windows, args.stage2_fraction, seconds_budget=budget)
         if i >= args.warmup:
             vals.append(v)
             total += dt
