@@ -264,7 +264,13 @@ def gold_cascade_60s():
     print("cascade_60s", len(windows), len(idx), summ)
 
 
-def gold_cascade_cfg2():
+def gold_cascade_second():
+    """An INDEPENDENT recording for the decision-parity test (tests/test_gpu_fullsize.py): 300 s at 48 kHz from another
+    generator seed (4242; 599 windows), same conditioned weights, thresholds 0.5 / 0.5 and 0.55 / 0.45.  ~15 min of CPU."""
+    gold_cascade_cfg2(seconds=300.0, seed=4242, name="cascade_300s_seed4242.npz", pairs=(("a", 0.5, 0.5), ("b", 0.55, 0.45)))
+
+
+def gold_cascade_cfg2(seconds=600.0, seed=2002, name="cascade_cfg2.npz", pairs=(("a", 0.5, 0.5), ("b", 0.6, 0.35))):
     """BASELINE.json configs[1] at FULL size: the 600-s 48 kHz recording the bench runs (synth.recording seed 2002) ->
     1199 windows through ref.forward_probs (Stage 1 on all, Stage 2 on the forwarded ones), the reference gate and
     ref.summarize_stage_outputs at thresholds 0.5 / 0.5 and at 0.6 / 0.35 (the counting quirk of SURVEY.md 0.7; its
@@ -274,7 +280,7 @@ def gold_cascade_cfg2():
     b1, b2 = float(g["head_bias1_s1"]), float(g["head_bias1_s2"])
     fx1 = T.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD)
     fx2 = T.hf_feature_extractor(synth.STAGE2_MEAN, synth.STAGE2_STD)
-    rec = synth.recording(600.0, 48000, seed=2002)
+    rec = synth.recording(seconds, 48000, seed=seed)
     audio = T.resample(rec, 48000, 16000)
     windows = ref.window_audio(audio, 1.0, 0.5)
     m1 = T.hf_model_from_state_dict(synth.random_state_dict(11, head_bias1=b1))
@@ -282,7 +288,7 @@ def gold_cascade_cfg2():
     s1 = ref.forward_probs(m1, fx1, windows, 16)
     out = {}
     s2_by_window = {}
-    for tag, thr1, thr2 in (("a", 0.5, 0.5), ("b", 0.6, 0.35)):
+    for tag, thr1, thr2 in pairs:
         preds = s1.argmax(axis=1)
         preds = np.where((preds == 1) & (s1[:, 1] >= thr1), 1, 0)   # ref:313-317
         idx = np.where(preds == 1)[0]
@@ -299,8 +305,8 @@ def gold_cascade_cfg2():
         out[f"summary_{tag}"] = json.dumps(summ)
         out[f"thresholds_{tag}"] = np.array([thr1, thr2])
         print("cascade_cfg2", tag, len(windows), len(idx), summ)
-    np.savez_compressed(os.path.join(GOLD, "cascade_cfg2.npz"), s1_probs=s1, head_bias1_s1=b1, head_bias1_s2=b2,
-                        n_windows=len(windows), audio16k_head=audio[:64], **out)
+    np.savez_compressed(os.path.join(GOLD, name), s1_probs=s1, head_bias1_s1=b1, head_bias1_s2=b2,
+                        n_windows=len(windows), audio16k_head=audio[:64], seconds=seconds, seed=seed, **out)
 
 
 def gold_stats():
@@ -437,3 +443,5 @@ if __name__ == "__main__":
             gold_cascade_60s()
         if "cascadecfg2" in todo:  # only on request (--only cascadecfg2): ~25 min of CPU
             gold_cascade_cfg2()
+        if "cascadesecond" in todo:  # only on request (--only cascadesecond): ~15 min of CPU
+            gold_cascade_second()

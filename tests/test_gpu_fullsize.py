@@ -98,14 +98,17 @@ def test_cfg2_stage2_equals_direct_forward(cfg2):
     assert np.abs(probs - res.s2_probs[sel]).max() <= 2e-3  # same kernels; the fused path normalises on the fly
 
 
-@pytest.mark.parametrize("tag", ["a", "b"])
-def test_cfg2_decisions_equal_the_reference_run(golden_dir, tag):
+@pytest.mark.parametrize("fixture,tag", [("cascade_cfg2.npz", "a"), ("cascade_cfg2.npz", "b"),
+                                         ("cascade_300s_seed4242.npz", "a"), ("cascade_300s_seed4242.npz", "b")])
+def test_cfg2_decisions_equal_the_reference_run(golden_dir, fixture, tag):
     """The headline configuration against the reference ITSELF: tests/golden/cascade_cfg2.npz holds what
     ref.window_audio / ref.forward_probs / the reference gate / ref.summarize_stage_outputs produced on the CPU for this
     very 600-s recording and these weights (scripts/make_golden.py::gold_cascade_cfg2, ~25 min of CPU), at thresholds
     0.5 / 0.5 (a) and 0.6 / 0.35 (b, the counting quirk of SURVEY.md 0.7).  Every integer of the result must be equal --
     the forwarded index list over all 1199 windows, the per-window classes, every count and ratio of the summary -- up
-    to the one window of this recording whose reference margin (4.8e-6) is inside fp32 platform noise (see TAU below)."""
+    to the one window of this recording whose reference margin (4.8e-6) is inside fp32 platform noise (see TAU below).
+    cascade_300s_seed4242.npz is the same for an INDEPENDENT 300-s recording (another generator seed, 599 windows,
+    thresholds 0.5 / 0.5 and 0.55 / 0.45; scripts/make_golden.py::gold_cascade_second)."""
     import json
     import os
 
@@ -115,19 +118,22 @@ def test_cfg2_decisions_equal_the_reference_run(golden_dir, tag):
     from zenker_audio_detection_b200.model import ZenkerASTForAudioClassification
     from zenker_audio_detection_b200.pipeline import TwoStagePipeline
 
-    g = np.load(os.path.join(golden_dir, "cascade_cfg2.npz"))
+    g = np.load(os.path.join(golden_dir, fixture))
+    seconds = float(g["seconds"]) if "seconds" in g.files else 600.0
+    seed = int(g["seed"]) if "seed" in g.files else 2002
+    NW = int(g["n_windows"])
     thr1, thr2 = (float(v) for v in g[f"thresholds_{tag}"])
     fx1 = ZenkerASTFeatureExtractor(mean=synth.STAGE1_MEAN, std=synth.STAGE1_STD)
     fx2 = ZenkerASTFeatureExtractor(mean=synth.STAGE2_MEAN, std=synth.STAGE2_STD)
     m1 = ZenkerASTForAudioClassification({"max_length": 1024}, synth.random_state_dict(11, head_bias1=float(g["head_bias1_s1"])))
     m2 = ZenkerASTForAudioClassification({"max_length": 1024}, synth.random_state_dict(22, head_bias1=float(g["head_bias1_s2"])))
     pipe = TwoStagePipeline(m1, fx1, m2, fx2, batch_size=128, stage1_threshold=thr1, stage2_threshold=thr2)
-    res = pipe.run_waveform(synth.recording(600.0, 48000, seed=2002), 48000)
-    assert res.num_windows == int(g["n_windows"]) == 1199
+    res = pipe.run_waveform(synth.recording(seconds, 48000, seed=seed), 48000)
+    assert res.num_windows == NW == int((seconds - 1.0) / 0.5) + 1
     ref_idx, ref_s2 = g[f"swallow_indices_{tag}"], g[f"s2_probs_{tag}"]
     p = g["s1_probs"].astype(np.float64)
     margin = np.log(p[:, 1]) - np.log(p[:, 0])
-    print(f"cfg2[{tag}] thr {thr1}/{thr2}: re-checked {res.rechecked_s1} + {res.rechecked_s2} windows; forwarded ours/ref "
+    print(f"{fixture}[{tag}] thr {thr1}/{thr2}: re-checked {res.rechecked_s1} + {res.rechecked_s2} windows; forwarded ours/ref "
           f"{len(res.swallow_indices)}/{len(ref_idx)}; max |p1 - ref| {np.abs(res.s1_probs - g['s1_probs']).max():.3g}; "
           f"smallest reference |margin - decision point| "
           f"{min(np.abs(margin - m).min() for m in pipe.margins1):.3g}")
@@ -136,23 +142,23 @@ def test_cfg2_decisions_equal_the_reference_run(golden_dir, tag):
     # fp32 evaluation is bound to reproduce -- this recording has ONE such window (4.8e-6 from the argmax point; the next
     # is at 2.4e-5).  Every other window must decide exactly as the reference did.
     TAU = 1e-5
-    ours_mask, ref_mask = np.zeros(1199, bool), np.zeros(1199, bool)
+    ours_mask, ref_mask = np.zeros(NW, bool), np.zeros(NW, bool)
     ours_mask[res.swallow_indices] = True
     ref_mask[ref_idx] = True
-    undecidable = np.zeros(1199, bool)
+    undecidable = np.zeros(NW, bool)
     for mg in pipe.margins1:
         undecidable |= np.abs(margin - mg) < TAU
     flips = ours_mask != ref_mask
     print(f"  windows within {TAU} of a Stage-1 decision point: {np.where(undecidable)[0].tolist()} "
           f"(margins {margin[undecidable].tolist()}); gate flips: {np.where(flips)[0].tolist()}")
-    assert int(undecidable.sum()) <= 1
+    assert int(undecidable.sum()) <= 3  # cfg2 has one such window, the 300-s recording two (neither of which flips)
     assert not (flips & ~undecidable).any()
     assert np.abs(res.s1_probs - g["s1_probs"]).max() <= 2.5e-3
     both = ours_mask & ref_mask
     ours2 = res.s2_probs[np.searchsorted(res.swallow_indices, np.where(both)[0])]
     ref2 = ref_s2[np.searchsorted(ref_idx, np.where(both)[0])]
     assert np.abs(ours2 - ref2).max() <= 2.5e-3
-    ref_classes = glue.stage2_classes(1199, [(int(i), q) for i, q in zip(ref_idx, ref_s2)], np.float32(thr2))
+    ref_classes = glue.stage2_classes(NW, [(int(i), q) for i, q in zip(ref_idx, ref_s2)], np.float32(thr2))
     assert np.array_equal(res.classes[~undecidable], ref_classes[~undecidable])
     ref_summary = json.loads(str(g[f"summary_{tag}"]))
     slack = int(undecidable.sum())  # each undecidable window may move one count by one
