@@ -185,3 +185,35 @@ def test_last_layer_tail_matches_full_layer(batch):
         full, _ = m.forward_features(feats, return_hidden=True)  # asking for the hidden state forces the full layer
         err = (pruned - full).abs().max().item()
         assert err <= 4e-3, (layers, err)
+
+
+def test_layernorm_tail_of_the_residual_gemms_is_bit_identical():
+    """ZK_LN_FUSE (north_star (4): LayerNorm fused into the GEMM that produces its input): bit 0 lets fc2 write the next
+    layer's layernorm_before output, bit 1 lets the out-projection write layernorm_after, both from extra warps of the
+    GEMM kernel while the rows are still in L2.  Same row arithmetic as the separate kernel, so logits and the whole
+    residual stream must be BIT-identical in every mode -- with the last layer pruned (logits) and unpruned (hidden).
+    The switch is read once per process, hence the subprocesses."""
+    import hashlib
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys, hashlib; sys.path.insert(0, %r)\n"
+        "from zenker_audio_detection_b200 import ops, synth\n"
+        "plan = ops.FbankPlan()\n"
+        "w = torch.from_numpy(synth.cfg1_windows(12)).cuda()\n"
+        "feats = plan.fx_contract(w, synth.STAGE1_MEAN, synth.STAGE1_STD, 1024)\n"
+        "m = ops.AstModel(synth.random_state_dict(5), num_layers=3)\n"
+        "l1 = m.forward_features(feats)\n"
+        "l2, hid = m.forward_features(feats, return_hidden=True)\n"
+        "torch.cuda.synchronize()\n"
+        "print('SUM', hashlib.sha256(l1.cpu().numpy().tobytes() + l2.cpu().numpy().tobytes() + hid.cpu().numpy().tobytes()).hexdigest(),"
+        " float(l1.abs().sum()))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sums = {}
+    for mode in ("0", "1", "2", "3"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ZK_LN_FUSE=mode), capture_output=True, text=True)
+        assert r.returncode == 0, (mode, r.stdout[-400:], r.stderr[-1500:])
+        sums[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("SUM")][0]
+    print(sums)
+    assert len(set(sums.values())) == 1, sums

@@ -50,6 +50,14 @@ struct Params {
   int w_off[MAX_PRODUCTS];     // same for W
   int out_plane_stride;        // ..._SPLIT epilogues: columns between the hi and lo output planes (= N)
   int seg_kb;                  // SEG kernels: k-blocks per accumulator chain
+  // LayerNorm tail (LNT kernels, N = 768 residual GEMMs): rows of the residual stream that all their column tiles have
+  // been reduce-added into are normalised by extra warps of the CTA that ran the LAST column tile, while they are
+  // still in L2, and written as the next GEMM's 16-bit A operand
+  const float* ln_w;
+  const float* ln_b;
+  uint16_t* ln_out;            // [M][768]
+  int* ln_count;               // [num_m_tiles][2]: epilogue-warp arrivals per (256-row tile, CTA of the pair); zeroed by the host
+  float ln_eps;
 };
 
 // PATCH epilogue only: one thread owns 32 consecutive columns [col0, col0+32) of row `row`; rows are scattered to
@@ -436,8 +444,10 @@ namespace pair {
 constexpr int STAGES2 = 5;
 constexpr int HALF_B_BYTES = 128 * BK * 2, STAGE2_BYTES = A_BYTES + HALF_B_BYTES;
 constexpr int OFF_STG2 = STAGES2 * STAGE2_BYTES, OFF_BAR2 = OFF_STG2 + EPI_WARPS * STG_BYTES;
+constexpr int OFF_LN2 = OFF_BAR2 + 256;                    // LNT kernels: gamma | beta (2 x 768 fp32)
 constexpr int SMEM2_BYTES = OFF_BAR2 + 256 + 1024;
-static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int SMEM2_LN_BYTES = OFF_LN2 + 2 * 768 * 4 + 1024;
+static_assert(SMEM2_LN_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address -> even CTA
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -489,12 +499,63 @@ __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
       : "memory");
 }
 
-template <int EPI, int FMT, bool SEG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+constexpr int LN_WARPS = 4, LN_ROW = 768;
+
+// One row of the residual stream -> LayerNorm -> 16-bit operand row.  The arithmetic is layernorm_kernel's (zk_ops.cu),
+// operation for operation, so the fused and the separate path give bit-identical results; x comes from L2 (ld.global.cg:
+// the TMA reduce-adds that produced it never touched this SM's L1), gamma / beta from shared memory.
+template <int FMT>
+__device__ __forceinline__ void ln_tail_rows2(const float* __restrict__ x, const float4* __restrict__ gw, const float4* __restrict__ gb,
+                                              float eps, uint16_t* __restrict__ out, long long row_a, long long row_b, bool has_b,
+                                              int lane) {
+  // two rows in flight per warp: all twelve 16-byte loads are issued before the first use
+  const float4* xa = reinterpret_cast<const float4*>(x + row_a * LN_ROW);
+  const float4* xb = reinterpret_cast<const float4*>(x + (has_b ? row_b : row_a) * LN_ROW);
+  float4 va[6], vb[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) va[i] = __ldcg(xa + lane + 32 * i);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) vb[i] = __ldcg(xb + lane + 32 * i);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    if (which == 1 && !has_b) break;
+    float4* v = which ? vb : va;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / LN_ROW);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      v[i].x -= mean;
+      v[i].y -= mean;
+      v[i].z -= mean;
+      v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / LN_ROW) + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + (which ? row_b : row_a) * LN_ROW);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 g = gw[lane + 32 * i];
+      const float4 bb = gb[lane + 32 * i];
+      const float y0 = v[i].x * rstd * g.x + bb.x, y1 = v[i].y * rstd * g.y + bb.y;
+      const float y2 = v[i].z * rstd * g.z + bb.z, y3 = v[i].w * rstd * g.w + bb.w;
+      uint2 o;
+      o.x = pack16<FMT>(y0, y1);
+      o.y = pack16<FMT>(y2, y3);
+      orow[lane + 32 * i] = o;
+    }
+  }
+}
+
+template <int EPI, int FMT, bool SEG, bool LNT = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS + (LNT ? LN_WARPS * 32 : 0), 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
   static_assert(EPI != ZK_EPI_PATCH_F32, "the patch-embedding epilogue stays on the single-CTA kernel");
   static_assert(!SEG || EPI == ZK_EPI_BIAS_RESID_F32, "segments are joined by the reduce-add of the residual epilogue");
+  static_assert(!LNT || (EPI == ZK_EPI_BIAS_RESID_F32 && !SEG), "the LayerNorm tail follows the one-product residual epilogue");
   constexpr uint32_t IDESC2 = umma_idesc_16(FMT, 2 * BM, BN, 0, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -503,11 +564,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = empty + STAGES2;                               // one per CTA
   uint64_t* tempty = tfull + 2;                                    // leader's copy is the live one (2 x 8 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float4* ln_gw = reinterpret_cast<float4*>(smem + OFF_LN2);        // LNT: gamma | beta, 2 x 768 floats
+  float4* ln_gb = ln_gw + LN_ROW / 4;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
+  if (LNT) {
+    for (int i = threadIdx.x; i < LN_ROW / 4; i += blockDim.x) {
+      ln_gw[i] = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
+      ln_gb[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
+    }
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -592,7 +661,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     const int quarter = warp & 3;         // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;     // which 128 accumulator columns
     uint8_t* stg = smem + OFF_STG2 + (warp - 2) * STG_BYTES;  // this warp's 32 x 128 B staging tile (1024-B aligned)
@@ -612,8 +681,43 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_leader(&tempty[acc]);
+      if (LNT && lane == 0) {
+        // the accumulator is already released; now wait until this warp's reduce-adds of the tile have LANDED (not
+        // just been read out of shared memory) and count the warp in for its 128 rows of the 256-row tile
+        bulk_wait0();
+        asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy (TMA) writes before the generic-proxy flag
+        __threadfence();
+        atomicAdd(p.ln_count + (m_blk * 2 + (int)rank), 1);
+      }
     }
     if (lane == 0) bulk_wait0();
+  } else if (LNT) {
+    // ------------------------------------------------------------------ LayerNorm tail (4 warps)
+    // The CTA that runs the last column tile of a 256-row tile normalises its own 128 rows once all 3 x 8 epilogue
+    // warps that add into them (this CTA's and, for the other column tiles, the same-rank CTAs of other clusters,
+    // which are resident and make progress on their own) have been counted in.
+    const int lw = warp - (2 + EPI_WARPS);
+    const int target = p.num_n_tiles * EPI_WARPS;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile - m_blk * p.num_n_tiles;
+      if (n_blk != p.num_n_tiles - 1) continue;
+      if (lane == 0) {
+        const int* cnt = p.ln_count + (m_blk * 2 + (int)rank);
+        int seen;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+          if (seen >= target) break;
+          __nanosleep(256);
+        }
+      }
+      __syncwarp();
+      const long long row0 = (long long)m_blk * 2 * BM + (long long)rank * BM;
+      for (int r = 2 * lw; r < BM; r += 2 * LN_WARPS) {
+        const long long ra = row0 + r, rb = ra + 1;
+        if (ra >= p.M) break;
+        ln_tail_rows2<FMT>(reinterpret_cast<const float*>(p.out), ln_gw, ln_gb, p.ln_eps, p.ln_out, ra, rb, rb < p.M, lane);
+      }
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -622,11 +726,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
-template <int EPI, int FMT, bool SEG = false>
+template <int EPI, int FMT, bool SEG = false, bool LNT = false>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p, int prof_cls,
                        cudaStream_t stream) {
+  constexpr int NTHREADS = THREADS + (LNT ? LN_WARPS * 32 : 0);
+  constexpr int NSMEM = LNT ? SMEM2_LN_BYTES : SMEM2_BYTES;
   static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI, FMT, SEG>), SMEM2_BYTES, &attr_done)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<EPI, FMT, SEG, LNT>), NSMEM, &attr_done)) return rc;
   // persistent grid = the number of CTA pairs the device can hold at once (a TPC with one usable SM cannot host a
   // pair, so this may be less than num_sms / 2); asked from the runtime once per device
   static int resident[64] = {0};
@@ -636,8 +742,8 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (cap == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (num_sms() / 2));
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = NSMEM;
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = 2;
@@ -646,7 +752,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.attrs = &at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI, FMT, SEG>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel<EPI, FMT, SEG, LNT>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = num_sms() / 2;
     }
@@ -657,7 +763,8 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = tiles < cap ? tiles : cap;
   ProfScope prof(prof_cls, stream);
-  gemm_pair_kernel<EPI, FMT, SEG><<<2 * clusters, THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmC, p);
+  if (LNT) ZK_CUDA(cudaMemsetAsync(p.ln_count, 0, (size_t)p.num_m_tiles * 2 * sizeof(int), stream));
+  gemm_pair_kernel<EPI, FMT, SEG, LNT><<<2 * clusters, NTHREADS, NSMEM, stream>>>(tmA, tmB, tmC, p);
   ZK_LAUNCH_CHECK("gemm_pair_kernel");
   return 0;
 }
@@ -676,6 +783,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return 0;
 }
 }  // namespace gemm
+
+bool gemm_ln_tail_ok(long long M) {
+  static const int use_pair = getenv("ZK_GEMM_PAIR") ? atoi(getenv("ZK_GEMM_PAIR")) : 2;
+  return use_pair && M >= 4 * gemm::BM;
+}
 
 int gemm16(const GemmArgs& g, cudaStream_t stream) {
   using namespace gemm;
@@ -751,6 +863,7 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
   p.acc_scale = g.acc_scale;
   p.nprod = g.products;
   p.out_plane_stride = N;
+  p.ln_w = g.ln_w, p.ln_b = g.ln_b, p.ln_out = reinterpret_cast<uint16_t*>(g.ln_out), p.ln_count = g.ln_count, p.ln_eps = g.ln_eps;
   if (g.products == 3) {  // smallest terms first: A_lo W_hi, A_hi W_lo, A_hi W_hi
     p.a_off[0] = K, p.w_off[0] = 0;
     p.a_off[1] = 0, p.w_off[1] = K;
@@ -769,7 +882,15 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
   // split-operand residual GEMMs: cut the K chain into segments joined by rounded adds (see SEG_KB)
   p.seg_kb = K >= SEG_LONG_K ? SEG_KB_LONG : SEG_KB;
   const bool seg = g.products == 3 && epilogue == ZK_EPI_BIAS_RESID_F32 && K % (BK * p.seg_kb) == 0 && K > BK * p.seg_kb;
-  if (use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2)) {
+  const bool pair_ok = use_pair && epilogue != ZK_EPI_PATCH_F32 && M >= 4 * BM && (epilogue != ZK_EPI_BIAS_GELU_BF16 || use_pair >= 2);
+  // LayerNorm tail asked for: only the one-product residual GEMM over full 768-wide rows on CTA-pair tiles has it
+  const bool ln_tail = g.ln_out != nullptr;
+  if (ln_tail && !(pair_ok && epilogue == ZK_EPI_BIAS_RESID_F32 && !seg && g.products == 1 && N == 768 && ldo == N && g.ln_w &&
+                   g.ln_b && g.ln_count)) {
+    set_error("gemm16: the LayerNorm tail needs the CTA-pair residual GEMM with N = 768, one product and M >= %d", 4 * BM);
+    return ZK_ERR_ARG;
+  }
+  if (pair_ok) {
     if ((rc = make_tmap_bf16_2d(&tmB, g.w, (uint64_t)N, (uint64_t)planes_in * K, (uint64_t)ldw, 128, BK))) return rc;  // half W tiles
     p.num_m_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
     switch (epilogue) {
@@ -781,6 +902,9 @@ int gemm16(const GemmArgs& g, cudaStream_t stream) {
                    : pair::launch_pair<ZK_EPI_BIAS_GELU_BF16, FMT_BF16>(tmA, tmB, tmC, p, cls(ZK_K_GEMM_FC1), stream);
       case ZK_EPI_BIAS_RESID_F32:
         if (seg) return pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16, true>(tmA, tmB, tmC, p, cls(cls_resid), stream);
+        if (ln_tail)
+          return f16 ? pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16, false, true>(tmA, tmB, tmC, p, cls(cls_resid), stream)
+                     : pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_BF16, false, true>(tmA, tmB, tmC, p, cls(cls_resid), stream);
         return f16 ? pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_F16>(tmA, tmB, tmC, p, cls(cls_resid), stream)
                    : pair::launch_pair<ZK_EPI_BIAS_RESID_F32, FMT_BF16>(tmA, tmB, tmC, p, cls(cls_resid), stream);
       case ZK_EPI_BIAS_SPLIT: return pair::launch_pair<ZK_EPI_BIAS_SPLIT, FMT_F16>(tmA, tmB, tmC, p, cls(ZK_K_RECHECK), stream);

@@ -27,8 +27,18 @@ struct GemmArgs {
   const float* aux = nullptr;
   int aux_rows = 0;
   int prof_cls = -1;
+  // optional LayerNorm tail (ZK_EPI_BIAS_RESID_F32 with N = 768 on the CTA-pair kernel only, see gemm_ln_tail_ok):
+  // ln_out [M][768] 16-bit in `fmt` = LayerNorm(out) with ln_w / ln_b / ln_eps, produced by the same kernel;
+  // ln_count = device scratch of gemm_ln_tail_counters(M) ints
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
+  void* ln_out = nullptr;
+  int* ln_count = nullptr;
+  float ln_eps = 0.f;
 };
 int gemm16(const GemmArgs& g, cudaStream_t stream);
+bool gemm_ln_tail_ok(long long M);                 // true when gemm16 can run the residual GEMM with the LayerNorm tail
+inline size_t gemm_ln_tail_counters(long long M) { return (size_t)((M + 255) / 256) * 2; }
 
 int attention16(const void* qkv, void* out, int batch, int tokens, int fmt, cudaStream_t stream);
 // re-check precision: qkv fp16 [rows][2*2304] (hi | lo planes of q|k|v) -> out fp16 [rows][2*768] (hi | lo)

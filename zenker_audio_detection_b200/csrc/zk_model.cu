@@ -21,6 +21,7 @@
 
 namespace {
 constexpr int HID = 768, MLP = 3072, QKV = 3 * HID, PATCH_K = 256;
+constexpr int ZK_LN_FUSE_DEFAULT = 0;  // set by measurement, see DESIGN.md section 6
 
 // One nn.Linear weight [N][K] as the kernels read it:
 //   planes  fp16 [N][2K] = hi | lo of W * 2^e (e chosen so that max |W| 2^e lies in (2^13, 2^14]: the lo plane stays in
@@ -105,6 +106,7 @@ static void carve(zk_model* m, uint8_t* base, size_t* total) {
 struct Workspace {
   float* x;
   uint16_t *h, *qkv, *mlp;
+  int* ln_count;  // scratch of the residual GEMMs' LayerNorm tail (zk_gemm.cu)
 };
 static size_t carve_ws(const zk_model* m, int batch, int planes, uint8_t* base, Workspace* ws) {
   Carver c{base, 0};
@@ -114,6 +116,7 @@ static size_t carve_ws(const zk_model* m, int batch, int planes, uint8_t* base, 
   w.h = c.take<uint16_t>(rows * HID * planes);
   w.qkv = c.take<uint16_t>(rows * QKV * planes);
   w.mlp = c.take<uint16_t>(rows * MLP * planes);
+  w.ln_count = c.take<int>(gemm_ln_tail_counters((long long)rows));
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -148,9 +151,13 @@ static int forward_impl(zk_model* m, const GatherSrc& src, int batch, int precis
   const long long rows = (long long)batch * m->tokens;
   const long long prow = (long long)batch * m->patches;
   // out = epilogue(A W^T): A has `planes` planes of K columns; W is read as the precision asks
+  // ln_w != nullptr: the residual GEMM also produces h = LayerNorm(out) (ln_w, ln_b) for the next GEMM (LayerNorm tail)
   auto gemm = [&](const void* a, const WeightDev& w, size_t w_row0, const float* bias, void* out, long long ldo, long long M,
-                  int N, int K, int epilogue, int prof_cls) {
+                  int N, int K, int epilogue, int prof_cls, const float* ln_w = nullptr, const float* ln_b = nullptr) {
     GemmArgs g;
+    if (ln_w) {
+      g.ln_w = ln_w, g.ln_b = ln_b, g.ln_out = ws.h, g.ln_count = ws.ln_count, g.ln_eps = m->ln_eps;
+    }
     g.a = a;
     g.lda = (long long)planes * K;
     if (!hp && m->fmt == FMT_BF16) {
@@ -187,19 +194,39 @@ static int forward_impl(zk_model* m, const GatherSrc& src, int batch, int precis
   static const bool full_last = getenv("ZK_FULL_LAST_LAYER") && atoi(getenv("ZK_FULL_LAST_LAYER")) != 0;
   const bool prune = !hp && !hidden && !full_last && m->num_layers >= 1;
   const int full_layers = prune ? m->num_layers - 1 : m->num_layers;
+  // LayerNorm fused into the residual GEMM that produces its input (north_star (4), zk_gemm.cu "LayerNorm tail"):
+  // ZK_LN_FUSE bit 0 = fc2 -> layernorm_before of the next layer, bit 1 = out-projection -> layernorm_after.
+  // FAST precision only; bit-identical to the separate kernel (same row arithmetic).
+  static const int ln_fuse_env = getenv("ZK_LN_FUSE") ? atoi(getenv("ZK_LN_FUSE")) : ZK_LN_FUSE_DEFAULT;
+  const int ln_fuse = (!hp && gemm_ln_tail_ok(rows)) ? ln_fuse_env : 0;
+  bool h_is_ln1 = false;  // ws.h already holds layernorm_before of the coming layer
   for (int l = 0; l < full_layers; ++l) {
     const LayerDev& L = m->layer[l];
-    if ((rc = layernorm16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, fmt, planes, -1, stream))) return rc;
+    if (!h_is_ln1 && (rc = layernorm16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, fmt, planes, -1, stream))) return rc;
+    h_is_ln1 = false;
     if ((rc = gemm(ws.h, L.qkv, 0, L.qkv_b, ws.qkv, (long long)planes * QKV, rows, QKV, HID, EPI_LIN, -1))) return rc;
     if (hp) {
       if ((rc = attention_split(ws.qkv, ws.h, batch, m->tokens, stream))) return rc;
     } else {
       if ((rc = attention16(ws.qkv, ws.h, batch, m->tokens, fmt, stream))) return rc;
     }
-    if ((rc = gemm(ws.h, L.o, 0, L.o_b, ws.x, 0, rows, HID, HID, ZK_EPI_BIAS_RESID_F32, -1))) return rc;
-    if ((rc = layernorm16(ws.x, L.ln2_w, L.ln2_b, m->ln_eps, ws.h, rows, HID, fmt, planes, -1, stream))) return rc;
+    if (ln_fuse & 2) {
+      // the tail overwrites ws.h (this GEMM's A operand) row block by row block, each only after every column tile of
+      // the block has run its whole K loop
+      if ((rc = gemm(ws.h, L.o, 0, L.o_b, ws.x, 0, rows, HID, HID, ZK_EPI_BIAS_RESID_F32, -1, L.ln2_w, L.ln2_b))) return rc;
+    } else {
+      if ((rc = gemm(ws.h, L.o, 0, L.o_b, ws.x, 0, rows, HID, HID, ZK_EPI_BIAS_RESID_F32, -1))) return rc;
+      if ((rc = layernorm16(ws.x, L.ln2_w, L.ln2_b, m->ln_eps, ws.h, rows, HID, fmt, planes, -1, stream))) return rc;
+    }
     if ((rc = gemm(ws.h, L.fc1, 0, L.fc1_b, ws.mlp, (long long)planes * MLP, rows, MLP, HID, EPI_GELU, -1))) return rc;
-    if ((rc = gemm(ws.mlp, L.fc2, 0, L.fc2_b, ws.x, 0, rows, HID, MLP, ZK_EPI_BIAS_RESID_F32, -1))) return rc;
+    const LayerDev* next = l + 1 < m->num_layers ? &m->layer[l + 1] : nullptr;  // (the pruned last layer starts with its LN1 too)
+    if ((ln_fuse & 1) && next) {
+      if ((rc = gemm(ws.mlp, L.fc2, 0, L.fc2_b, ws.x, 0, rows, HID, MLP, ZK_EPI_BIAS_RESID_F32, -1, next->ln1_w, next->ln1_b)))
+        return rc;
+      h_is_ln1 = true;
+    } else {
+      if ((rc = gemm(ws.mlp, L.fc2, 0, L.fc2_b, ws.x, 0, rows, HID, MLP, ZK_EPI_BIAS_RESID_F32, -1))) return rc;
+    }
   }
   if (!prune) {
     if (hidden) ZK_CUDA(cudaMemcpyAsync(hidden, ws.x, (size_t)rows * HID * 4, cudaMemcpyDeviceToDevice, stream));
@@ -216,7 +243,7 @@ static int forward_impl(zk_model* m, const GatherSrc& src, int batch, int precis
     uint16_t* att2 = c.take<uint16_t>((size_t)r2 * HID);
     uint16_t* mlp2 = c.take<uint16_t>((size_t)r2 * MLP);
     float* x2 = c.take<float>((size_t)r2 * HID);
-    if ((rc = layernorm16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, fmt, 1, -1, stream))) return rc;
+    if (!h_is_ln1 && (rc = layernorm16(ws.x, L.ln1_w, L.ln1_b, m->ln_eps, ws.h, rows, HID, fmt, 1, -1, stream))) return rc;
     // K | V projections of every token, written in place into columns [768, 2304) of the fused QKV buffer
     if ((rc = gemm(ws.h, L.qkv, HID, L.qkv_b + HID, ws.qkv + HID, QKV, rows, 2 * HID, HID, ZK_EPI_BIAS_BF16, ZK_K_GEMM_QKV)))
       return rc;
