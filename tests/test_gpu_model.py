@@ -192,7 +192,8 @@ def test_layernorm_tail_of_the_residual_gemms_is_bit_identical():
     layer's layernorm_before output, bit 1 lets the out-projection write layernorm_after, both from extra warps of the
     GEMM kernel while the rows are still in L2.  Same row arithmetic as the separate kernel, so logits and the whole
     residual stream must be BIT-identical in every mode -- with the last layer pruned (logits) and unpruned (hidden).
-    The switch is read once per process, hence the subprocesses."""
+    80 windows = 380 row tiles, i.e. ~15 tiles per CTA pair, so the hand-over between CTAs is exercised across many
+    tiles.  The switch is read once per process, hence the subprocesses."""
     import hashlib
     import subprocess
     import sys
@@ -201,7 +202,7 @@ def test_layernorm_tail_of_the_residual_gemms_is_bit_identical():
         "import torch, sys, hashlib; sys.path.insert(0, %r)\n"
         "from zenker_audio_detection_b200 import ops, synth\n"
         "plan = ops.FbankPlan()\n"
-        "w = torch.from_numpy(synth.cfg1_windows(12)).cuda()\n"
+        "w = torch.from_numpy(synth.cfg1_windows(80)).cuda()\n"
         "feats = plan.fx_contract(w, synth.STAGE1_MEAN, synth.STAGE1_STD, 1024)\n"
         "m = ops.AstModel(synth.random_state_dict(5), num_layers=3)\n"
         "l1 = m.forward_features(feats)\n"
