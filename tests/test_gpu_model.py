@@ -187,6 +187,35 @@ def test_last_layer_tail_matches_full_layer(batch):
         assert err <= 4e-3, (layers, err)
 
 
+@pytest.mark.parametrize("max_length", [256, 112])
+def test_other_max_length_geometries(max_length):
+    """ASTConfig.max_length is a checkpoint property (HF:configuration...: max_length, ref:91-93 passes the config
+    through): a model fine-tuned on max_length 256 has 2 + 12 * 25 = 302 tokens, one on 112 has 122 -- fewer than one
+    query tile, with ragged key blocks and row tiles in every kernel.  Full 3-layer forward at both precisions against
+    the fp32 oracle, and through the fused fbank gather (frames beyond the window are the pad constant)."""
+    from zenker_audio_detection_b200 import _lib, ops, synth
+
+    tokens = 2 + 12 * ((max_length - 16) // 10 + 1)
+    sd = synth.random_state_dict(31)
+    g = torch.Generator().manual_seed(max_length)
+    sd["audio_spectrogram_transformer.embeddings.position_embeddings"] = torch.randn(1, tokens, 768, generator=g) * 0.02
+    plan = ops.FbankPlan()
+    w = torch.from_numpy(synth.cfg1_windows(9)).cuda()
+    feats = plan.fx_contract(w, synth.STAGE1_MEAN, synth.STAGE1_STD, max_length)
+    assert feats.shape == (9, max_length, 128)
+    m = ops.AstModel(sd, max_length=max_length, num_layers=3)
+    assert m.tokens == tokens
+    ref, ref_hidden = _oracle_logits(sd, feats, num_layers=3, return_hidden=True)
+    fast, hidden = m.forward_features(feats, return_hidden=True)
+    pruned = m.forward_features(feats)
+    hi = m.forward_features(feats, precision=_lib.PRECISION_RECHECK)
+    e_fast, e_pruned, e_hi = ((t - ref).abs().max().item() for t in (fast, pruned, hi))
+    rel = ((hidden - ref_hidden).norm() / ref_hidden.norm()).item()
+    print(f"max_length {max_length} ({tokens} tokens): fast {e_fast:.3g}, pruned {e_pruned:.3g}, re-check {e_hi:.3g}, hidden rel {rel:.3g}")
+    assert e_fast <= 5e-3 and e_pruned <= 5e-3 and rel <= 3e-3, (e_fast, e_pruned, rel)
+    assert e_hi <= 5e-5, e_hi
+
+
 def test_layernorm_tail_of_the_residual_gemms_is_bit_identical():
     """ZK_LN_FUSE (north_star (4): LayerNorm fused into the GEMM that produces its input): bit 0 lets fc2 write the next
     layer's layernorm_before output, bit 1 lets the out-projection write layernorm_after, both from extra warps of the
