@@ -735,13 +735,29 @@ def run_cfg4(args):
     seconds = [float(v) for v in rng.uniform(lo, hi, size=R)]
     lengths = [int(round(sec * 48000)) for sec in seconds]
     patients = [[2 * i, 2 * i + 1] for i in range(R // 2)]
-    shards = zdist.shard_recordings(lengths, world)
-    mine = shards[rank]
+    # window counts per recording (48 -> 16 kHz: ceil(n / 3) samples; ref:62-75)
+    counts = [max(1, (-(-n // 3) - 16000) // 8000 + 1) for n in lengths]
     pipe, sd1 = build_pipeline(args, device)
     calib = torch.from_numpy(synth.recording(120.0, 48000, seed=4000)).to(device)  # the same on every rank
     calibrate_gate(pipe, sd1, calib, args.stage2_fraction, device)
     del calib
-    hosts = {i: torch.from_numpy(synth.recording(seconds[i], 48000, seed=4100 + i)).pin_memory() for i in mine}
+    hosts = {}
+
+    def host(i):  # pinned host copy of recording i, made on first use (the plan may change once, see below)
+        if i not in hosts:
+            hosts[i] = torch.from_numpy(synth.recording(seconds[i], 48000, seed=4100 + i)).pin_memory()
+        return hosts[i]
+
+    def plan(weights=None):
+        if args.shard == "windows":   # runs of windows: whole recordings plus at most one partial one at either end
+            return zdist.shard_window_ranges(counts, world, weights=weights)
+        # whole recordings, longest first (the reference launcher's granularity)
+        return [[(i, 0, counts[i]) for i in sh] for sh in zdist.shard_recordings(lengths, world)]
+
+    shards = plan()
+    mine = shards[rank]
+    for c in mine:
+        host(c[0])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -752,9 +768,9 @@ def run_cfg4(args):
     def one_step():
         t0 = time.perf_counter()
         blocks, n, k, re = [], 0, 0, 0
-        for i in mine:
-            r = pipe.run_waveform(hosts[i], 48000)
-            blocks.append(zdist.pack_records(i, r.s1_probs, r.swallow_indices, r.s2_probs))
+        for i, w0, w1 in mine:
+            r = pipe.run_waveform(host(i), 48000, window_range=(w0, w1))
+            blocks.append(zdist.pack_records(i, r.s1_probs, r.swallow_indices, r.s2_probs, window_base=w0))
             n += r.num_windows
             k += len(r.swallow_indices)
             re += r.rechecked_s1 + r.rechecked_s2
@@ -767,9 +783,25 @@ def run_cfg4(args):
             docs = zdist.patient_documents(zdist.unpack_records(allrec), patients, pipe.thr2, pipe.stage2_argmax)
         return busy, time.perf_counter() - t0, n, k, re, allrec, docs
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        if mine:
-            pipe.run_waveform(hosts[mine[0]], 48000)
+    # Warm-up = whole untimed steps on the equal plan.  The GPUs of one box settle at different power-capped clocks (busy
+    # times of EQUAL runs differ by +-3 %), so with --balance speed the last warm-up step's busy times are all-gathered and
+    # the runs re-cut in proportion to each rank's measured windows/s -- the records do not depend on where the cuts are.
+    speeds = None
+    warm_busy = 0.0
+    for _ in range(max(1, min(args.warmup, 3))):
+        sync_all()
+        warm_busy = one_step()[0]
+    if args.shard == "windows" and args.balance == "speed" and world > 1:
+        mine_speed = torch.tensor([sum(c[2] - c[1] for c in mine) / max(warm_busy, 1e-6)], dtype=torch.float64, device=device)
+        allspeed = torch.zeros((world,), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allspeed, mine_speed)
+        speeds = [float(v) for v in allspeed.cpu()]
+        if not all(v > 0 for v in speeds):  # a rank without work (more ranks than windows): keep the equal plan
+            speeds = None
+        shards = plan(speeds)
+        mine = shards[rank]
+        for c in mine:
+            host(c[0])
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     busy_s, wall_s, n_tot, k_tot, re_tot = 0.0, 0.0, 0, 0, 0
@@ -792,11 +824,12 @@ def run_cfg4(args):
     else:
         allstats[0] = stats
     allstats = allstats.cpu().numpy()
-    # bit-identity across ranks: re-run the first recording of the NEXT rank's shard here and compare with what it sent
+    # bit-identity across ranks and across the split: re-run, UNSPLIT, the recording the NEXT rank's shard starts with
+    # (with window sharding that is normally the one cut between this rank and the next) and compare with what was gathered
     ok = 1
     other = shards[(rank + 1) % world]
     if world > 1 and other:
-        i = other[0]
+        i = other[0][0]
         r = pipe.run_waveform(torch.from_numpy(synth.recording(seconds[i], 48000, seed=4100 + i)).pin_memory(), 48000)
         mine_rec = zdist.pack_records(i, r.s1_probs, r.swallow_indices, r.s2_probs)
         theirs = allrec[allrec[:, 0] == i]
@@ -813,23 +846,30 @@ def run_cfg4(args):
             "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": pipe.m1.operand_format, "data": "synthetic",
             "config": {"workload": f"cfg4: patient-level batch, a fixed pool of {R} synthetic 48 kHz recordings of U({lo:.0f},{hi:.0f}) s "
-                                   f"({R // 2} patients x 2 files) sharded longest-first over {world} GPU(s), one gather per step",
+                                   f"({R // 2} patients x 2 files) sharded over {world} GPU(s) "
+                                   + ("in runs of windows" if args.shard == "windows" else "by recording, longest first")
+                                   + ", one gather per step",
                        "batch_size": args.batch_size, "windows_per_step": n_all // args.steps,
                        "stage2_fraction": round(float(allstats[:, 3].sum()) / max(1, n_all), 4),
                        "l2": "activation working set >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": n_all / (step_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(sum(lengths) * 4),
+            "e2e": {"value": n_all / (step_ms / 1000.0), "unit": UNIT,
+                    "h2d_bytes_per_step": int(sum(lengths[c[0]] for sh in shards for c in sh) * 4),  # a split recording is copied by both ranks
                     "d2h_bytes_per_step": int(n_all // args.steps * 12 + float(allstats[:, 3].sum()) / args.steps * 12),
                     "note": "this workload is timed end to end only: every recording starts in pinned host memory"},
             "gpu_launches": None,
             "clocks": clk.summary(),
-            "sharding": {"recordings_per_rank": [len(s) for s in shards],
-                         "audio_seconds_per_rank": [round(sum(seconds[i] for i in s), 1) for s in shards],
+            "sharding": {"granularity": args.shard, "balance": ("speed" if speeds else "equal") if args.shard == "windows" else None,
+                         "probe_windows_per_s_per_rank": [round(v, 1) for v in speeds] if speeds else None,
+                         "chunks_per_rank": [len(sh) for sh in shards],
+                         "windows_per_rank": [sum(c[2] - c[1] for c in sh) for sh in shards],
+                         "split_recordings": len({c[0] for sh in shards for c in sh if (c[1], c[2]) != (0, counts[c[0]])}),
                          "busy_ms_per_rank_per_step": [round(float(v), 2) for v in busy],
                          "imbalance_max_over_mean": float(busy.max() / busy.mean()),
                          "gather_and_join_ms_per_step": round(step_ms / args.steps - float(busy.max()), 2),
-                         "what_sets_the_gap": "the slowest rank's busy time (longest-first sharding leaves at most one recording "
-                                              "of imbalance; the GPUs also run at different power-capped clocks); the gather is "
-                                              "24 B per window"},
+                         "what_sets_the_gap": "the slowest rank's busy time: equal runs of windows differ only by the data-dependent "
+                                              "Stage-2 / re-check counts (recording granularity leaves up to one recording of "
+                                              "imbalance), and the GPUs run at different power-capped clocks; the gather is 24 B "
+                                              "per window"},
             "rechecked_windows_per_step": float(allstats[:, 4].sum()) / args.steps,
             "records_bit_identical_across_ranks": bool(int(okt.item()) == 1) if world > 1 else None,
             "patients": len(docs) if docs is not None else None,
@@ -855,6 +895,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--pool", type=int, default=64, help="cfg4: recordings in the fixed pool (2 per patient)")
     ap.add_argument("--pool-seconds", default="90,150", help="cfg4: recording lengths are U(lo,hi) seconds")
+    ap.add_argument("--shard", default="windows", choices=["windows", "recordings"],
+                    help="cfg4: runs of windows (dist.shard_window_ranges) or whole recordings, longest first")
+    ap.add_argument("--balance", default="speed", choices=["speed", "equal"],
+                    help="cfg4 --shard windows: runs proportional to each GPU's measured probe speed, or equal")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

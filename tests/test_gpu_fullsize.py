@@ -241,6 +241,30 @@ def test_cfg4_results_do_not_depend_on_order_or_rank():
             assert np.array_equal(x, y)
 
 
+def test_cfg4_a_recording_split_into_window_ranges_gives_the_same_records():
+    """dist.shard_window_ranges cuts the pool into equal runs of windows, so a recording can be classified in two (or
+    more) pieces on different ranks: `run_waveform(..., window_range=(w0, w1))` must give those windows BIT for bit what
+    the unsplit run gives (same samples -> same frames -> same features; batch composition does not matter)."""
+    from zenker_audio_detection_b200 import dist as zdist, synth
+    from zenker_audio_detection_b200._lib import ZkError
+
+    pipe = _pipeline(64)
+    rec = synth.recording(47.0, 48000, seed=4321)
+    whole = pipe.run_waveform(rec, 48000)
+    n = whole.num_windows
+    assert n == 93
+    ref = zdist.pack_records(5, whole.s1_probs, whole.swallow_indices, whole.s2_probs)
+    for cuts in ([0, 31, n], [0, 1, 64, 65, n], [0, n]):
+        blocks = []
+        for w0, w1 in zip(cuts[:-1], cuts[1:]):
+            r = pipe.run_waveform(rec, 48000, window_range=(w0, w1))
+            assert r.num_windows == w1 - w0
+            blocks.append(zdist.pack_records(5, r.s1_probs, r.swallow_indices, r.s2_probs, window_base=w0))
+        assert np.array_equal(np.concatenate(blocks), ref), cuts
+    with pytest.raises(ZkError):
+        pipe.run_waveform(rec, 48000, window_range=(10, n + 1))
+
+
 def test_cfg5_batch32_forward_is_batch_invariant_and_matches_the_fp32_oracle():
     """cfg5: (32, 1024, 128) features ~ N(0, 0.5), seed 5005, 1214 tokens, 16-bit weights.  The
     32-window forward equals four 8-window forwards and thirty-two single-window forwards bit for bit (tile shapes do

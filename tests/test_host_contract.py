@@ -94,6 +94,50 @@ def test_shard_recordings_is_balanced_and_deterministic():
     assert zdist.shard_recordings([5], 4) == [[0], [], [], []]
 
 
+def test_shard_window_ranges_cover_every_window_once_in_equal_runs():
+    rng = np.random.default_rng(2)
+    counts = rng.integers(150, 1300, size=64).tolist() + [1, 0, 7]
+    for ws in (1, 2, 3, 8):
+        shards = zdist.shard_window_ranges(counts, ws)
+        per = [sum(b - a for _, a, b in s) for s in shards]
+        assert sum(per) == sum(counts) and max(per) - min(per) <= 1          # equal runs of windows
+        seen = {}
+        for s in shards:
+            assert s == sorted(s)
+            for i, a, b in s:
+                seen.setdefault(i, []).append((a, b))
+        for i, c in enumerate(counts):                                       # every window exactly once, in order
+            pieces = sorted(seen.get(i, []))
+            assert (pieces == []) if c == 0 else (pieces[0][0] == 0 and pieces[-1][1] == c)
+            assert all(pieces[k][1] == pieces[k + 1][0] for k in range(len(pieces) - 1))
+        assert sum(1 for i in seen if len(seen[i]) > 1) <= ws - 1            # at most one cut between neighbouring ranks
+        assert shards == zdist.shard_window_ranges(counts, ws)
+    assert zdist.shard_window_ranges([1], 4) == [[], [], [], [(0, 0, 1)]]
+    # proportional runs: a rank that measured 10 % more windows/s gets 10 % more windows; same coverage rules
+    w = [1.0, 1.1, 0.9, 1.0]
+    shards = zdist.shard_window_ranges(counts, 4, weights=w)
+    per = [sum(b - a for _, a, b in s) for s in shards]
+    assert sum(per) == sum(counts)
+    assert all(abs(p - sum(counts) * wi / sum(w)) <= 1.0 for p, wi in zip(per, w))
+    assert zdist.shard_window_ranges(counts, 4, weights=[2.0] * 4) == zdist.shard_window_ranges(counts, 4)
+    with pytest.raises(ValueError):
+        zdist.shard_window_ranges(counts, 4, weights=[1.0, 0.0, 1.0, 1.0])
+
+
+def test_records_of_a_split_recording_merge_back():
+    rng = np.random.default_rng(3)
+    s1 = rng.random((37, 2)).astype(np.float32)
+    idx = np.array([0, 5, 6, 30, 36], dtype=np.int64)
+    s2 = rng.random((5, 2)).astype(np.float32)
+    whole = zdist.pack_records(7, s1, idx, s2)
+    cut = 6   # windows 0..5 on one rank, 6..36 on the next; Stage-2 indices are relative to the chunk
+    a = zdist.pack_records(7, s1[:cut], idx[idx < cut], s2[idx < cut])
+    b = zdist.pack_records(7, s1[cut:], idx[idx >= cut] - cut, s2[idx >= cut], window_base=cut)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    got = zdist.unpack_records(np.concatenate([b, a]))[7]
+    assert np.array_equal(got[0], s1) and np.array_equal(got[1], idx) and np.array_equal(got[2], s2)
+
+
 def test_record_pack_unpack_roundtrip():
     rng = np.random.default_rng(1)
     s1 = rng.random((37, 2)).astype(np.float32)

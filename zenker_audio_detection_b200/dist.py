@@ -9,7 +9,7 @@ carried as an int32 matrix (the float words bit-cast), so ids and probabilities 
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -32,8 +32,47 @@ def shard_recordings(lengths: Sequence[int], world_size: int) -> List[List[int]]
     return shards
 
 
-def pack_records(recording_id: int, s1_probs: np.ndarray, swallow_indices: np.ndarray, s2_probs: np.ndarray) -> np.ndarray:
-    """-> (n, 6) int32 record block of one recording (see the module docstring)."""
+def shard_window_ranges(window_counts: Sequence[int], world_size: int,
+                        weights: Optional[Sequence[float]] = None) -> List[List[Tuple[int, int, int]]]:
+    """Finer than ``shard_recordings``: the windows of all recordings, laid end to end in recording order, are cut into
+    ``world_size`` runs, so a rank gets ``(recording, first_window, end_window)`` chunks -- whole recordings plus at
+    most one partial recording at either end of its run.  A window's scores do not depend on which other windows
+    share its batch or its fbank (``TwoStagePipeline.run_audio16k(window_range=...)``; tested bit-exactly), so a split
+    recording gives the same records as an unsplit one.  Runs are equal (to one window) by default; ``weights`` (one
+    positive number per rank, e.g. the windows/s each GPU measured on a common probe -- the GPUs of a box settle at
+    different power-capped clocks) makes them proportional instead.  Deterministic given its arguments: every rank
+    must pass the same ``weights`` (all-gather them first)."""
+    total = int(sum(int(c) for c in window_counts))
+    if weights is None:
+        bounds = [(r * total) // world_size for r in range(world_size + 1)]
+    else:
+        w = [float(v) for v in weights]
+        if len(w) != world_size or not all(v > 0 and v == v and v != float("inf") for v in w):
+            raise ValueError("weights: one positive finite number per rank")
+        acc, cum = 0.0, [0.0]
+        for v in w:
+            acc += v
+            cum.append(acc)
+        bounds = [min(total, int(total * c / acc + 1e-9)) for c in cum]
+        bounds[0], bounds[-1] = 0, total
+        for r in range(1, world_size + 1):
+            bounds[r] = max(bounds[r], bounds[r - 1])
+    shards: List[List[Tuple[int, int, int]]] = [[] for _ in range(world_size)]
+    base = 0
+    for i, c in enumerate(window_counts):
+        c = int(c)
+        for r in range(world_size):
+            lo, hi = max(bounds[r], base), min(bounds[r + 1], base + c)
+            if lo < hi:
+                shards[r].append((i, lo - base, hi - base))
+        base += c
+    return shards
+
+
+def pack_records(recording_id: int, s1_probs: np.ndarray, swallow_indices: np.ndarray, s2_probs: np.ndarray,
+                 window_base: int = 0) -> np.ndarray:
+    """-> (n, 6) int32 record block of one recording, or of its windows ``window_base ...`` (a chunk of
+    ``shard_window_ranges``; ``swallow_indices`` are relative to the chunk).  See the module docstring."""
     n = len(s1_probs)
     f = np.full((n, 4), np.nan, dtype=np.float32)
     f[:, 0:2] = s1_probs
@@ -41,7 +80,7 @@ def pack_records(recording_id: int, s1_probs: np.ndarray, swallow_indices: np.nd
         f[swallow_indices, 2:4] = s2_probs
     rec = np.empty((n, RECORD_WIDTH), dtype=np.int32)
     rec[:, 0] = recording_id
-    rec[:, 1] = np.arange(n, dtype=np.int32)
+    rec[:, 1] = np.arange(window_base, window_base + n, dtype=np.int32)
     rec[:, 2:6] = f.view(np.int32)
     return rec
 

@@ -130,8 +130,20 @@ class TwoStagePipeline:
             ops.scatter_rows2(hi, pos, r, logits)
         return r
 
-    def run_audio16k(self, audio: torch.Tensor) -> RecordingResult:
-        """``audio``: CUDA float32 mono 16 kHz (what ``load_audio`` returns, ref:53-59)."""
+    def run_audio16k(self, audio: torch.Tensor, window_range: Optional[Sequence[int]] = None) -> RecordingResult:
+        """``audio``: CUDA float32 mono 16 kHz (what ``load_audio`` returns, ref:53-59).
+
+        ``window_range = (w0, w1)`` runs the cascade on windows ``w0 .. w1-1`` of the recording only (a chunk of
+        ``dist.shard_window_ranges``): window ``k`` is samples ``[k hop, k hop + win)`` (ref:62-75) and its features are
+        frames of those samples alone, so the slice ``[w0 hop, (w1-1) hop + win)`` gives those windows bit for bit;
+        indices in the result are relative to ``w0``."""
+        if window_range is not None:
+            w0, w1 = int(window_range[0]), int(window_range[1])
+            _, _, n_all = cascade.window_geometry(int(audio.numel()), self.window_sec, self.hop_sec)
+            if not 0 <= w0 < w1 <= n_all:
+                raise ZkError(f"window_range {(w0, w1)} outside the recording's {n_all} windows")
+            if (w0, w1) != (0, n_all):
+                audio = audio[w0 * self.hop:(w1 - 1) * self.hop + self.win]
         with torch.cuda.device(self.device):
             L = int(audio.numel())
             _, _, n = cascade.window_geometry(L, self.window_sec, self.hop_sec)
@@ -212,9 +224,12 @@ class TwoStagePipeline:
                 w = (w if w.is_pinned() else w.pin_memory()).to(self.device, non_blocking=True)
             return ops.resample(w, int(sample_rate), SAMPLING_RATE)
 
-    def run_waveform(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int) -> RecordingResult:
-        """``waveform``: host (or device) ``(channels, n)`` / ``(n,)`` float32, or ``(n, channels)`` int16 PCM."""
-        return self.run_audio16k(self.resample_to_device(waveform, sample_rate))
+    def run_waveform(self, waveform: Union[np.ndarray, torch.Tensor], sample_rate: int,
+                     window_range: Optional[Sequence[int]] = None) -> RecordingResult:
+        """``waveform``: host (or device) ``(channels, n)`` / ``(n,)`` float32, or ``(n, channels)`` int16 PCM.  The whole
+        recording is resampled (the 41-tap filter sees the same neighbours as in an unsplit run) even when only
+        ``window_range`` of it is classified."""
+        return self.run_audio16k(self.resample_to_device(waveform, sample_rate), window_range)
 
     def run_patient(self, waveforms: Sequence[Union[np.ndarray, torch.Tensor]], sample_rates: Sequence[int],
                     names: Optional[Sequence[str]] = None) -> Dict[str, Any]:
