@@ -212,3 +212,68 @@ def test_wav_prefetcher_keeps_order_and_reraises():
     assert pf.get("a") == ("A", 16000)  # exhausted: synchronous
     pf.close()
     assert calls.count("d") == 1 and calls[:3] == ["a", "bad", "c"]
+
+
+def test_wav_prefetcher_extend_keeps_prefetching():
+    from zenker_audio_detection_b200.batch import WavPrefetcher
+
+    seen = []
+
+    def reader(path):
+        seen.append(path)
+        return path.upper(), 48000
+
+    pf = WavPrefetcher([], reader=reader)       # the dynamic schedule starts empty and learns its files claim by claim
+    pf.extend(["a", "b"])
+    assert pf.get("a") == ("A", 48000)
+    pf.extend(["c"])
+    assert pf.get("b") == ("B", 48000) and pf.get("c") == ("C", 48000)
+    pf.extend(["d"])
+    assert pf.get("d") == ("D", 48000)
+    pf.close()
+    assert seen == ["a", "b", "c", "d"]          # each file decoded once, in order
+
+
+def _claim_worker(rank, world, port, n, q):
+    import random
+    import time
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = []
+    rnd = random.Random(rank)
+    for i in batch.claim_indices(n, rank, world, "dynamic"):
+        got.append(i)
+        time.sleep((0.03 if rank else 0.005) * (1 + rnd.random()))  # rank 1 is the slow GPU
+    dist.barrier()
+    q.put((rank, got))
+    dist.destroy_process_group()
+
+
+def test_dynamic_schedule_claims_every_patient_exactly_once():
+    """`batch --schedule dynamic`: ranks take the next unclaimed patient from a counter in the process group's store, so
+    the queue is covered exactly once whatever the ranks' speeds, and the slow rank ends up with fewer patients."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n = 23
+    procs = [ctx.Process(target=_claim_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(outs[0] + outs[1]) == list(range(n))
+    assert outs[0] == sorted(outs[0]) and outs[1] == sorted(outs[1])   # each rank walks the queue front to back
+    assert len(outs[0]) > len(outs[1]) > 0
+    assert list(batch.claim_indices(5, 0, 1)) == [0, 1, 2, 3, 4]
+    assert [list(batch.claim_indices(5, r, 2, "static", sizes=[9, 1, 8, 2, 7])) for r in range(2)] == [[0, 1, 3], [2, 4]]

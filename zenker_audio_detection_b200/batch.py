@@ -95,6 +95,12 @@ class WavPrefetcher:
             self._pending = (self._paths[self._next], self._pool.submit(self._reader, self._paths[self._next]))
             self._next += 1
 
+    def extend(self, paths: Sequence[str]) -> None:
+        """Append more files to the plan (the dynamic schedule learns its patients one claim at a time)."""
+        self._paths.extend(paths)
+        if self._pending is None:
+            self._submit()
+
     def get(self, path: str):
         if self._pending is not None and self._pending[0] == path:
             fut = self._pending[1]
@@ -145,6 +151,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
     ap.add_argument("--extra", help="accepted for compatibility; ignored")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("--schedule", default="dynamic", choices=["dynamic", "static"],
+                    help="under torchrun: ranks claim patients from a shared longest-first queue (default), or take a fixed "
+                         "longest-first partition")
     return ap
 
 
@@ -171,12 +180,24 @@ def global_plan(args) -> Tuple[List[Tuple[str, List[str], int]], List[str]]:
     return todo, log
 
 
+def plan_queue(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str]]], List[str]]:
+    """-> (the WHOLE work queue ``[(patient, [file_a, file_b])]``, longest first, identical on every rank; log lines):
+    what the dynamic schedule claims from (``claim_indices``).  Made on rank 0 and broadcast like ``plan_patients``."""
+    todo, log = _global_plan_everywhere(args, rank, world)
+    return [(pid, files) for pid, files, _ in sorted(todo, key=lambda t: (-t[2], t[0]))], log
+
+
 def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str]]], List[str]]:
-    """-> (this rank's ``[(patient, [file_a, file_b])]``, log lines).
+    """-> (this rank's ``[(patient, [file_a, file_b])]``, log lines): the static longest-first partition.
 
     With more than one rank the plan is made by rank 0 alone and broadcast: a rank that started late would otherwise see
     result files an early rank has already written, skip those patients, shard a DIFFERENT list and drop or duplicate
     work.  The exchange goes over a gloo group (host objects); ranks then shard the identical list longest-first."""
+    todo, log = _global_plan_everywhere(args, rank, world)
+    return shard_plan(todo, rank, world), log
+
+
+def _global_plan_everywhere(args, rank: int, world: int):
     if world > 1:
         import torch.distributed as dist
 
@@ -187,7 +208,34 @@ def plan_patients(args, rank: int, world: int) -> Tuple[List[Tuple[str, List[str
         todo, log = box[0]
     else:
         todo, log = global_plan(args)
-    return shard_plan(todo, rank, world), log
+    return todo, log
+
+
+def claim_indices(n: int, rank: int, world: int, schedule: str = "dynamic", sizes: Optional[Sequence[int]] = None,
+                  key: str = "zk_batch_next"):
+    """Yields the positions of a queue of ``n`` work items that THIS rank is to process.
+
+    ``dynamic`` (more than one rank): self-scheduling -- every rank takes the next unclaimed position from a shared
+    counter in the process group's key-value store (``store.add`` is atomic), so a GPU that runs at a lower power-capped
+    clock, or that drew the long recordings, simply claims fewer patients; with the queue ordered longest-first the
+    ranks finish within one patient of each other.  No collective, no rank waits for another.  ``static``: the fixed
+    longest-first partition of ``dist.shard_recordings`` over ``sizes`` (what a dry run prints)."""
+    if world <= 1:
+        yield from range(n)
+        return
+    if schedule == "static":
+        from .dist import shard_recordings
+
+        yield from shard_recordings(list(sizes) if sizes is not None else [1] * n, world)[rank]
+        return
+    import torch.distributed as dist
+
+    store = dist.distributed_c10d._get_default_store()
+    while True:
+        i = int(store.add(key, 1)) - 1
+        if i >= n:
+            return
+        yield i
 
 
 def shard_plan(todo, rank: int, world: int) -> List[Tuple[str, List[str]]]:
@@ -211,13 +259,21 @@ def run(args, rank: int = 0, world: int = 1) -> int:
     s2_root = args.stage2_model_root or default_model_root(2, args.fold)
     out_dir = args.output_dir or "outputs"
     os.makedirs(out_dir, exist_ok=True)
-    mine, log = plan_patients(args, rank, world)
+    dynamic = getattr(args, "schedule", "dynamic") == "dynamic" and world > 1
+    mine, log = plan_queue(args, rank, world) if dynamic else plan_patients(args, rank, world)
     if rank == 0:
         for line in log:
             print(line)
-    for pid, files in mine:
-        print(f"[RUN] rank {rank}: {pid}  A: {files[0]}  B: {files[1]}")
-    if args.dry_run or not mine:
+    if dynamic:
+        queue = mine
+        if rank == 0:
+            for pid, files in queue:
+                print(f"[QUEUE] {pid}  A: {files[0]}  B: {files[1]}")
+    else:
+        queue = mine
+        for pid, files in mine:
+            print(f"[RUN] rank {rank}: {pid}  A: {files[0]}  B: {files[1]}")
+    if args.dry_run or not queue:
         return 0
 
     import torch
@@ -248,8 +304,27 @@ def run(args, rank: int = 0, world: int = 1) -> int:
     if not args.disable_cache and args.feature_cache_dir:
         cache_dir = os.path.abspath(args.feature_cache_dir)
     failures = 0
-    wavs = WavPrefetcher([p for _, files in mine for p in files])
-    for pid, files in mine:
+    # This rank's patients in the order it takes them: its static share, or claims from the shared queue.  One patient is
+    # claimed AHEAD of the one being processed so that its first file decodes on the host while the GPU works.
+    claims = claim_indices(len(queue), rank, world, "dynamic") if dynamic else iter(range(len(queue)))
+    wavs = WavPrefetcher([])
+    if dynamic:  # start claiming together: a rank whose models loaded first would otherwise drain a short queue alone
+        import torch.distributed as dist
+
+        dist.barrier()
+
+    def take():
+        i = next(claims, None)
+        if i is None:
+            return None
+        wavs.extend(queue[i][1])
+        return queue[i]
+
+    ahead = take()
+    while ahead is not None:
+        (pid, files), ahead = ahead, take()
+        if dynamic:
+            print(f"[RUN] rank {rank}: {pid}  A: {files[0]}  B: {files[1]}")
         try:
             summaries = []
             for path in files:
@@ -272,6 +347,10 @@ def run(args, rank: int = 0, world: int = 1) -> int:
             failures += 1
             print(f"[ERROR] patient {pid}: {type(e).__name__}: {e}")
     wavs.close()
+    if dynamic:  # rank 0 hosts the store the others claim from: nobody leaves before the queue is empty everywhere
+        import torch.distributed as dist
+
+        dist.barrier()
     print("Batch complete." if world == 1 else f"Batch complete (rank {rank}).")
     return failures
 
