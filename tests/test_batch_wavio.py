@@ -277,3 +277,62 @@ def test_dynamic_schedule_claims_every_patient_exactly_once():
     assert len(outs[0]) > len(outs[1]) > 0
     assert list(batch.claim_indices(5, 0, 1)) == [0, 1, 2, 3, 4]
     assert [list(batch.claim_indices(5, r, 2, "static", sizes=[9, 1, 8, 2, 7])) for r in range(2)] == [[0, 1, 3], [2, 4]]
+
+
+def test_all_folds_launcher_follows_the_shell_script(tmp_path, capsys, monkeypatch):
+    """python -m zenker_audio_detection_b200.folds = src/run_all_folds_simple_batch.sh in one process: LONG_AUDIO_ROOT from
+    the environment / the project's .env / the fallback (:22-42), flags in any order with unknown ones warned about
+    (:52-82), per-fold model roots, output directory and threshold config (:93-121), folds 1..5 in order."""
+    from zenker_audio_detection_b200 import folds
+
+    root = tmp_path / "proj"
+    long_root, _ = _tree(tmp_path)
+    ids = root / "data_ast_stage2"
+    ids.mkdir(parents=True)
+    for f in folds.FOLDS:
+        (ids / f"test_ids_fold{f}.txt").write_text("Healthy/224\n" if f % 2 else "Zenker/301\n")
+    (root / ".env").write_text(f"# paths\nexport OTHER=1\nLONG_AUDIO_ROOT=\"{long_root}\"\n")
+    (root / "runs").mkdir()
+    (root / "runs" / "optimal_thresholds_per_fold_both_stages.json").write_text(
+        json.dumps({"folds": {"1": {"stage1": {"threshold": 0.7}, "stage2": {"threshold": 0.2}}}}))
+    monkeypatch.delenv("LONG_AUDIO_ROOT", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert folds.read_env_file(str(root / ".env")) == {"OTHER": "1", "LONG_AUDIO_ROOT": str(long_root)}
+
+    cwd = os.getcwd()
+    assert folds.main(["--stage2-argmax", "runs", "--bogus", "--dry-run", "--stage1-forward-min-prob", "0.8",
+                       "--project-root", str(root)]) == 0
+    assert os.getcwd() == cwd
+    cap = capsys.readouterr()
+    out = cap.out
+    assert "Warning: Unknown option --bogus" in cap.err
+    assert f"Long audio directory: {long_root}" in out and "Using models from: runs" in out
+    assert f"Found threshold config: {root / 'runs' / 'optimal_thresholds_per_fold_both_stages.json'}" in out
+    assert (root / "runs" / "results" / "patient_inference").is_dir()
+    marks = [out.index(f"================ Fold {f} ================") for f in folds.FOLDS]
+    assert marks == sorted(marks) and out.rstrip().endswith("All folds completed.")
+    assert out.count("[RUN] rank 0: 224") == 3 and out.count("[RUN] rank 0: 301") == 2   # folds 1,3,5 / 2,4
+
+    opts = folds.parse(["exp/v1", "--no-threshold-config"])
+    argv = folds.fold_argv(opts, 4, str(root), "/data/long")
+    a = batch.build_arg_parser().parse_args(argv)
+    assert a.fold == 4 and a.long_audio_root == "/data/long" and a.pattern == "*.wav" and a.plot and not a.dry_run
+    assert a.stage1_model_root == str(root / "exp/v1" / "ast_classifier_stage1" / "fold4" / "best")
+    assert a.stage2_model_root == str(root / "exp/v1" / "ast_classifier_stage2" / "fold4" / "best")
+    assert a.output_dir == str(root / "exp/v1" / "results" / "patient_inference")
+    assert a.threshold_config is None and a.stage1_forward_min_prob is None and not a.stage2_argmax
+    b = batch.build_arg_parser().parse_args(folds.fold_argv(folds.parse(["--stage1-forward-min-prob", "0.8", "--stage2-argmax"]),
+                                                            1, str(root), "/data/long"))
+    assert b.threshold_config == str(root / "runs" / "optimal_thresholds_per_fold_both_stages.json")
+    assert b.stage1_forward_min_prob == 0.8 and b.stage2_argmax
+
+    # precedence of LONG_AUDIO_ROOT: environment, then .env, then the script's fallback
+    monkeypatch.setenv("LONG_AUDIO_ROOT", "/from/env")
+    folds.main(["--dry-run", "--project-root", str(root)])
+    assert "Long audio directory: /from/env" in capsys.readouterr().out
+    monkeypatch.delenv("LONG_AUDIO_ROOT")
+    (root / ".env").unlink()
+    folds.main(["--dry-run", "--project-root", str(root)])
+    out = capsys.readouterr().out
+    assert "Warning: LONG_AUDIO_ROOT not set" in out and f"Using fallback: {folds.FALLBACK_LONG_AUDIO_ROOT}" in out

@@ -247,7 +247,12 @@ def shard_plan(todo, rank: int, world: int) -> List[Tuple[str, List[str]]]:
     return [(todo[i][0], todo[i][1]) for i in mine]
 
 
+_RUN_SEQ = 0  # run() calls in this process; every rank makes the same calls, so it names the claim counter of a call
+
+
 def run(args, rank: int = 0, world: int = 1) -> int:
+    global _RUN_SEQ
+    _RUN_SEQ += 1
     cfg = None
     if args.threshold_config and os.path.exists(args.threshold_config):
         with open(args.threshold_config, "r") as f:
@@ -306,7 +311,8 @@ def run(args, rank: int = 0, world: int = 1) -> int:
     failures = 0
     # This rank's patients in the order it takes them: its static share, or claims from the shared queue.  One patient is
     # claimed AHEAD of the one being processed so that its first file decodes on the host while the GPU works.
-    claims = claim_indices(len(queue), rank, world, "dynamic") if dynamic else iter(range(len(queue)))
+    claims = (claim_indices(len(queue), rank, world, "dynamic", key=f"zk_batch_next/{_RUN_SEQ}/fold{args.fold}") if dynamic
+              else iter(range(len(queue))))
     wavs = WavPrefetcher([])
     if dynamic:  # start claiming together: a rank whose models loaded first would otherwise drain a short queue alone
         import torch.distributed as dist
