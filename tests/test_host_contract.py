@@ -272,3 +272,42 @@ def test_stats_aggregate_matches_the_reference_function(golden_dir):
     assert stats.finish(0.0, 0.0, 0) == {"mean": 0.0, "std": 0.0, "count": 0}
     f = stats.finish(10.0, 30.0, 4)
     assert f["mean"] == 2.5 and abs(f["std"] - ((30.0 / 4 - 6.25) * 4 / 3) ** 0.5) < 1e-15
+
+
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference checkout only exists in the build container")
+@pytest.mark.parametrize("script", ["test_long_audio_windows_2stage.py"])  # (the cached script shares load_stage_model; ~45 s each)
+def test_launcher_runs_the_unmodified_reference_script_up_to_the_device(tmp_path, script):
+    """`python -m zenker_audio_detection_b200.run <reference script>` in the one place the reference sources exist (no
+    GPU here; tests/test_gpu_pipeline.py holds the GPU half, which needs both): the script is executed unmodified -- its
+    own argparse takes its own flags -- and its `load_stage_model` (ref:86-98) reaches OUR classes through
+    `from transformers import ...` and stops at their loud no-CPU-path error, not inside HF's CPU model."""
+    import subprocess
+    import sys
+
+    from safetensors.torch import save_file
+    from transformers import ASTConfig
+
+    from oracle import thirdparty
+    from zenker_audio_detection_b200 import synth, wavio
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(REF_SRC, script)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    root = tmp_path / "s"
+    root.mkdir()
+    ASTConfig(num_labels=2).save_pretrained(str(root))
+    save_file({k: v.contiguous() for k, v in synth.random_state_dict(11).items()}, str(root / "model.safetensors"))
+    thirdparty.hf_feature_extractor(synth.STAGE1_MEAN, synth.STAGE1_STD).save_pretrained(str(root))
+    files = []
+    for i in range(2):
+        p = tmp_path / f"f{i}.wav"
+        wavio.write_pcm16(str(p), synth.recording(2.0, 16000, seed=60 + i)[None], 16000)
+        files.append(str(p))
+    r = subprocess.run([sys.executable, "-m", "zenker_audio_detection_b200.run", path, "--stage1-model-root", str(root),
+                        "--stage2-model-root", str(root), "--file-a", files[0], "--file-b", files[1], "--output-json",
+                        str(tmp_path / "out.json")], cwd=repo, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and not os.path.exists(tmp_path / "out.json")
+    assert "ZkError" in r.stderr and "load_stage_model" in r.stderr, r.stderr[-2000:]
