@@ -336,3 +336,38 @@ def test_all_folds_launcher_follows_the_shell_script(tmp_path, capsys, monkeypat
     folds.main(["--dry-run", "--project-root", str(root)])
     out = capsys.readouterr().out
     assert "Warning: LONG_AUDIO_ROOT not set" in out and f"Using fallback: {folds.FALLBACK_LONG_AUDIO_ROOT}" in out
+
+
+REF_EXTRACT = "/root/reference/utils/extract_thresholds_per_fold.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXTRACT), reason="the reference checkout only exists in the build container")
+def test_threshold_config_written_by_the_reference_tool_is_read_per_fold(tmp_path):
+    """Upstream of the path: `utils/extract_thresholds_per_fold.py`, unmodified, writes
+    optimal_thresholds_per_fold_both_stages.json from validation ROC/PR metrics (:93-122); `batch.resolve_thresholds`
+    must pick each fold's own pair out of exactly that file (run_batch:97-118), and `folds.fold_argv` must find it."""
+    import subprocess
+    import sys
+
+    from zenker_audio_detection_b200 import folds
+
+    def metrics(base):
+        return {"fold_reports": [{"fold": f, "best_f1_threshold": base + 0.01 * f, "best_f1": 0.9, "best_f1_precision": 0.8,
+                                  "best_f1_recall": 0.95} for f in (1, 2, 3, 4, 5)],
+                "aggregate": {"best_f1_threshold": base, "best_f1": 0.88, "best_f1_precision": 0.8, "best_f1_recall": 0.9}}
+
+    (tmp_path / "m1.json").write_text(json.dumps(metrics(0.60)))
+    (tmp_path / "m2.json").write_text(json.dumps(metrics(0.30)))
+    runs = tmp_path / "runs"
+    runs.mkdir()
+    cfg_path = runs / "optimal_thresholds_per_fold_both_stages.json"
+    r = subprocess.run([sys.executable, REF_EXTRACT, "--stage1-metrics", str(tmp_path / "m1.json"), "--stage2-metrics",
+                        str(tmp_path / "m2.json"), "--output-config", str(cfg_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and cfg_path.exists(), r.stderr[-1500:]
+    cfg = json.load(open(cfg_path))
+    for f in (1, 2, 3, 4, 5):
+        t1, t2 = batch.resolve_thresholds(cfg, f)
+        assert t1 == pytest.approx(0.60 + 0.01 * f) and t2 == pytest.approx(0.30 + 0.01 * f)
+    assert batch.resolve_thresholds(cfg, 9) == (None, None)      # a fold the file does not know keeps the CLI defaults
+    argv = folds.fold_argv(folds.parse(["runs"]), 2, str(tmp_path), "/data/long")
+    assert batch.build_arg_parser().parse_args(argv).threshold_config == str(cfg_path)
