@@ -311,3 +311,47 @@ def test_launcher_runs_the_unmodified_reference_script_up_to_the_device(tmp_path
                         str(tmp_path / "out.json")], cwd=repo, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and not os.path.exists(tmp_path / "out.json")
     assert "ZkError" in r.stderr and "load_stage_model" in r.stderr, r.stderr[-2000:]
+
+
+def test_shard_window_ranges_properties():
+    """Property test (hypothesis): for any pool and any positive weights every window is dealt exactly once, in order,
+    with at most one cut between neighbouring ranks, and a split recording's records merge back to the unsplit ones."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(0, 60), min_size=1, max_size=12), st.integers(1, 9), st.data())
+    def check(counts, world, data):
+        weights = data.draw(st.one_of(st.none(), st.lists(st.floats(0.2, 5.0), min_size=world, max_size=world)))
+        shards = zdist.shard_window_ranges(counts, world, weights=weights)
+        assert len(shards) == world
+        flat = [c for s in shards for c in s]
+        assert flat == sorted(flat)                                   # rank order == recording / window order
+        covered = {}
+        for i, a, b in flat:
+            assert 0 <= a < b <= counts[i]
+            assert covered.get(i, 0) == a                             # contiguous, no gap, no overlap
+            covered[i] = b
+        assert all(covered.get(i, 0) == c for i, c in enumerate(counts))
+        per = [sum(b - a for _, a, b in s) for s in shards]
+        if weights is None:
+            assert max(per) - min(per) <= 1
+        else:
+            tot, wsum = sum(counts), sum(weights)
+            assert all(abs(p - tot * w / wsum) <= 1.0 + 1e-6 for p, w in zip(per, weights))
+        # records of the pieces == records of the whole
+        rng = np.random.default_rng(len(flat))
+        blocks, whole = [], []
+        for i, c in enumerate(counts):
+            s1 = rng.random((c, 2)).astype(np.float32)
+            idx = np.where(s1[:, 1] > 0.6)[0].astype(np.int64)
+            s2 = rng.random((len(idx), 2)).astype(np.float32)
+            whole.append(zdist.pack_records(i, s1, idx, s2))
+            for j, a, b in flat:
+                if j == i:
+                    sel = (idx >= a) & (idx < b)
+                    blocks.append(zdist.pack_records(i, s1[a:b], idx[sel] - a, s2[sel], window_base=a))
+        w = np.concatenate(whole) if whole else np.zeros((0, 6), np.int32)
+        p = np.concatenate(blocks) if blocks else np.zeros((0, 6), np.int32)
+        assert np.array_equal(w, p)
+
+    check()
