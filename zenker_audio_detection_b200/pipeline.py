@@ -130,6 +130,38 @@ class TwoStagePipeline:
             ops.scatter_rows2(hi, pos, r, logits)
         return r
 
+    # ------------------------------------------------------------------ re-check band of a new checkpoint
+    def measure_fast_margin_error(self, audio: torch.Tensor, max_windows: int = 64) -> Dict[str, float]:
+        """``max |(l1 - l0)_fast - (l1 - l0)_recheck|`` per stage over the first ``max_windows`` windows of ``audio`` (CUDA
+        float32 mono 16 kHz): the quantity ``recheck_eps`` has to exceed for the gate to decide as the fp32 reference does
+        (DESIGN.md 4b).  The default band is sized on the conditioned random-init weights of the tests; a trained
+        checkpoint has its own error level, and this is how to read it off a few windows of real audio."""
+        with torch.cuda.device(self.device):
+            L = int(audio.numel())
+            _, _, n = cascade.window_geometry(L, self.window_sec, self.hop_sec)
+            if L < self.win:
+                audio = torch.cat([audio, torch.zeros(self.win - L, dtype=torch.float32, device=audio.device)])
+            n = min(n, int(max_windows))
+            audio = audio[:(n - 1) * self.hop + self.win].contiguous()
+            fbank = self.plan.fbank(audio) if self.fused else None
+            out = {}
+            for name, model, fx in (("stage1", self.m1, self.fx1), ("stage2", self.m2, self.fx2)):
+                if model.num_labels != 2:
+                    continue
+                fast = self._stage_logits(model, fx, audio, fbank, n, None)
+                slow = self._stage_logits(model, fx, audio, fbank, n, None, precision=_lib.PRECISION_RECHECK,
+                                          batch_size=self.recheck_batch)
+                out[name] = float(((fast[:, 1] - fast[:, 0]) - (slow[:, 1] - slow[:, 0])).abs().max().item())
+            return out
+
+    def calibrate_recheck_eps(self, audio: torch.Tensor, max_windows: int = 64, safety: float = 2.0) -> float:
+        """Widen ``recheck_eps`` to ``safety`` x the measured fast-path margin error if that exceeds the current band (it
+        is never narrowed); returns the band in force.  The drop-in ``__call__`` of the two models follows."""
+        err = self.measure_fast_margin_error(audio, max_windows)
+        self.recheck_eps = max(self.recheck_eps, float(safety) * max(err.values(), default=0.0))
+        self.m1.recheck_eps = self.m2.recheck_eps = self.recheck_eps
+        return self.recheck_eps
+
     def run_audio16k(self, audio: torch.Tensor, window_range: Optional[Sequence[int]] = None) -> RecordingResult:
         """``audio``: CUDA float32 mono 16 kHz (what ``load_audio`` returns, ref:53-59).
 
