@@ -61,6 +61,36 @@ def test_wav_other_encodings_are_normalised_like_torchaudio(tmp_path, tag, bits,
     assert np.array_equal(data[0], want)
 
 
+def test_wav_read_delivers_into_the_callers_buffer(tmp_path):
+    """read(path, alloc=...): the samples arrive in the array the caller hands out (the batch runner hands out page-locked
+    memory, batch.read_pinned), same values as the plain read; an array of another shape or dtype is refused."""
+    x = _tone(3001, 2, 7)
+    p = str(tmp_path / "a.wav")
+    wavio.write_pcm16(p, x, 48000)
+    plain, _ = wavio.read(p)
+    given = []
+
+    def alloc(shape, dtype):
+        backing = np.zeros(int(np.prod(shape)) * np.dtype(dtype).itemsize + 64, dtype=np.uint8)  # a larger foreign buffer
+        given.append(backing[:int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape))
+        return given[-1]
+
+    data, sr = wavio.read(p, alloc=alloc)
+    assert sr == 48000 and data is given[0] and np.array_equal(data, plain)
+    f = tmp_path / "f.wav"
+    raw = x[0].astype("<f4").tobytes()
+    with open(f, "wb") as fh:
+        fh.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE")
+        fh.write(b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 16000, 64000, 4, 32))
+        fh.write(b"data" + struct.pack("<I", len(raw)) + raw)
+    data, sr = wavio.read(str(f), alloc=alloc)
+    assert data is given[1] and data.shape == (1, 3001) and np.array_equal(data[0], x[0])
+    with pytest.raises(wavio.WavError):
+        wavio.read(p, alloc=lambda shape, dtype: np.empty(shape, dtype=np.float32))
+    with pytest.raises(wavio.WavError):
+        wavio.read(str(f), alloc=lambda shape, dtype: np.empty((shape[1], shape[0]), dtype=dtype))
+
+
 def test_wav_rejects_garbage(tmp_path):
     p = tmp_path / "c.wav"
     p.write_bytes(b"RIFF\x00\x00\x00\x00WAVEfmt ")

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import struct
 from dataclasses import dataclass
-from typing import BinaryIO, Tuple, Union
+from typing import BinaryIO, Callable, Optional, Tuple
 
 import numpy as np
 
@@ -84,15 +84,21 @@ def info(path: str) -> WavInfo:
         return _read_header(f)
 
 
-def read(path: str) -> Tuple[Union[np.ndarray], int]:
+def read(path: str, alloc: Optional[Callable[[Tuple[int, int], str], np.ndarray]] = None) -> Tuple[np.ndarray, int]:
     """-> ``(samples, sample_rate)``.  PCM16: int16 ``(frames, channels)`` (interleaved, as stored); everything else:
-    float32 ``(channels, frames)`` in [-1, 1) like ``torchaudio.load`` (ref:54)."""
+    float32 ``(channels, frames)`` in [-1, 1) like ``torchaudio.load`` (ref:54).
+
+    ``alloc(shape, dtype)`` (``dtype`` "<i2" or "<f4") supplies the array the samples are delivered in -- the batch
+    runner hands out page-locked memory, so the file is read straight into the buffer the H2D copy starts from."""
+    alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype=dtype))
     with open(path, "rb") as f:
         wi = _read_header(f)
         f.seek(wi.data_offset)
         n, c = wi.num_frames, wi.num_channels
         if wi.encoding == "PCM_S" and wi.bits_per_sample == 16:
-            pcm = np.empty((n, c), dtype="<i2")  # read straight into the (writable) array handed to the H2D copy
+            pcm = alloc((n, c), "<i2")  # read straight into the (writable) array handed to the H2D copy
+            if pcm.shape != (n, c) or pcm.dtype != np.dtype("<i2") or not pcm.flags.c_contiguous:
+                raise WavError("alloc() must return a C-contiguous array of the requested shape and dtype")
             got = f.readinto(memoryview(pcm).cast("B"))
             if got != wi.data_bytes:
                 raise WavError(f"{path}: short read ({got} of {wi.data_bytes} bytes)")
@@ -110,7 +116,11 @@ def read(path: str) -> Tuple[Union[np.ndarray], int]:
         x = np.frombuffer(raw, dtype="<f4").astype(np.float32)
     else:
         x = np.frombuffer(raw, dtype="<f8").astype(np.float32)
-    return np.ascontiguousarray(x.reshape(n, c).T), wi.sample_rate
+    out = alloc((c, n), "<f4")
+    if out.shape != (c, n) or out.dtype != np.dtype("<f4"):
+        raise WavError("alloc() must return an array of the requested shape and dtype")
+    out[...] = x.reshape(n, c).T
+    return out, wi.sample_rate
 
 
 def write_pcm16(path: str, samples: np.ndarray, sample_rate: int) -> None:
