@@ -18,7 +18,16 @@ $(LIBDIR)/libzk_b200.so: $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -shared -o $@ $(OBJS) -cudart shared
 
+# A plain C99 host that drives the path through the C ABI alone (no Python, no torch); needs a B200 to RUN.
+CUDA_HOME ?= /usr/local/cuda
+example: build/cascade_host
+build/cascade_host: examples/cascade_host.c include/zk_b200.h $(LIBDIR)/libzk_b200.so
+	@mkdir -p build
+	gcc -std=c99 -O2 -Wall -Wextra -pedantic -Iinclude -isystem $(CUDA_HOME)/include $< -o $@ \
+	    -L$(LIBDIR) -lzk_b200 -L$(CUDA_HOME)/lib64 -lcudart -lm \
+	    -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,$(CUDA_HOME)/lib64
+
 clean:
 	rm -rf build $(LIBDIR)/libzk_b200.so
 
-.PHONY: all clean
+.PHONY: all clean example

@@ -80,3 +80,15 @@ def test_product_never_imports_the_oracle():
                 # tables.py builds the constant tables with torch ops; compat.py imports torchaudio only to REBIND
                 # torchaudio.load / torchaudio.info to the RIFF reader -- no torchaudio compute anywhere in the product
                 assert "torchaudio" not in src or fn in ("tables.py", "compat.py") or "import torchaudio" not in src, fn
+
+
+def test_a_plain_c_host_builds_against_the_header_and_fails_loudly_without_a_gpu(c_host_binary):
+    """examples/cascade_host.c (C99, -Wall -Wextra -pedantic -Werror) compiles against include/zk_b200.h and links the
+    in-tree library: the header is C, not C++ or torch.  Without an sm_100 device the program stops at zk_device_check
+    with a message and a non-zero exit code -- it never computes anything on the CPU."""
+    import subprocess
+
+    if torch.cuda.is_available():
+        pytest.skip("the GPU run of the example is tests/test_gpu_abi_errors.py::test_plain_c_host_runs_the_cascade")
+    r = subprocess.run([c_host_binary, "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "zk_device_check" in r.stderr and "cascade_host:" not in r.stdout, (r.stdout, r.stderr)

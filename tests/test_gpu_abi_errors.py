@@ -166,3 +166,19 @@ def test_gate_and_band_select_checks(lib):
     win = torch.empty(n, dtype=torch.int32, device="cuda")
     rc = lib.zk_band_select(logits.data_ptr(), n, margins, 5, 0.01, None, pos.data_ptr(), win.data_ptr(), cnt.data_ptr(), _stream())
     assert rc in (ERR_ARG, ERR_SHAPE) and "4" in _msg(lib)      # at most four decision points per stage
+
+
+def test_plain_c_host_runs_the_cascade(c_host_binary):
+    """examples/cascade_host.c on the GPU: a C99 program with no Python and no torch in the process resamples a stereo
+    PCM16 recording and runs the whole two-stage cascade through zk_resample_pcm16 + zk_cascade_run, and its own checks
+    (window count of ref:62-75, probabilities summing to one, gate mask and ascending index list as functions of the
+    returned probabilities, ref:312-320) hold: exit code 0."""
+    import re
+    import subprocess
+
+    r = subprocess.run([c_host_binary, "12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    m = re.search(r"-> (\d+) windows, (\d+) forwarded to stage 2 .* checks ok", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) == 23 and 0 <= int(m.group(2)) <= 23      # 12 s at hop 0.5 s -> 23 windows
+    print(r.stdout.strip())
